@@ -1,0 +1,150 @@
+/*
+ * itrails_b200.h — C ABI of libitrails_b200.so (hand-written CUDA, sm_100a).
+ *
+ * The reference (trails-phylogeny/itrails) is pure Python and has no FFI layer; its
+ * boundary for the coalescent-HMM hot path is a set of Python functions.  Each entry
+ * point below names the reference function it replaces (paths relative to
+ * /root/reference/src/itrails).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add to call these instead of the Python/numba
+ * implementations.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - Every function returns 0 on success or a negative itr_status; the message is
+ *     available from itr_last_error(ctx) (never NULL).  No exceptions cross the ABI.
+ *   - Host buffers are caller-owned.  Device buffers live inside the opaque context
+ *     and are released by itr_destroy.  One context drives one GPU; a context is not
+ *     thread-safe.  Multi-GPU = one process (and context) per GPU; the only exchange
+ *     is the scalar sum of log-likelihood partials, which the host side performs with
+ *     an NCCL all-reduce (itrails_b200/distributed.py).
+ *   - All floating point is IEEE binary64.  Matrices are row-major.
+ *   - Symbols are the reference's observed-state indices 0..624
+ *     (read_data.py:6-24: nucleotide order A,C,T,G; 256.. contain at least one N).
+ *   - There is NO CPU fallback: every compute entry point fails with
+ *     ITR_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef ITRAILS_B200_H
+#define ITRAILS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct itr_ctx itr_ctx;
+
+enum itr_status {
+    ITR_OK = 0,
+    ITR_ERR_ARG = -1,      /* invalid argument (message says which)            */
+    ITR_ERR_STATE = -2,    /* call order violated (e.g. loglik before set_model) */
+    ITR_ERR_CUDA = -3,     /* CUDA runtime error / no usable device            */
+    ITR_ERR_NOMEM = -4,    /* host or device allocation failed                 */
+    ITR_ERR_UNSUPPORTED = -5
+};
+
+#define ITR_N_SYMBOLS 625   /* read_data.py:6-24 */
+#define ITR_N_PLAIN 256
+#define ITR_MAX_STATES 255  /* uint8 Viterbi backpointers / paths */
+
+/* ---- lifetime ------------------------------------------------------------------ */
+
+/* Create a context bound to CUDA device `device` (ordinal as seen by this process). */
+int itr_create(int device, itr_ctx **out);
+void itr_destroy(itr_ctx *ctx);
+/* Message of the last failing call on this context ("" if none).  With ctx == NULL,
+ * returns the message of the last failing itr_create in this thread. */
+const char *itr_last_error(const itr_ctx *ctx);
+/* Library/ABI version (major*1000 + minor). */
+int itr_version(void);
+
+/* ---- alignment blocks ------------------------------------------------------------
+ * Replaces the `V_lst` argument every reference wrapper takes (list of int64 arrays,
+ * one per MAF block, from read_data.py:94-117 maf_parser).  `sym` holds the blocks
+ * back to back as uint16; block b is sym[block_offsets[b] .. block_offsets[b+1]).
+ * One host->device copy; blocks are scheduled longest-first on the device.
+ * Every block must have at least one column. */
+int itr_load_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *block_offsets,
+                    int64_t n_blocks);
+/* Same, from int64 symbols exactly as maf_parser returns them (values checked). */
+int itr_load_blocks_i64(itr_ctx *ctx, const int64_t *sym, const int64_t *block_offsets,
+                        int64_t n_blocks);
+
+/* ---- model -----------------------------------------------------------------------
+ * Accepts (a, b, pi) as returned by the reference's trans_emiss_calc
+ * (get_trans_emiss.py:8-170): a is n_sets x K x K, b is n_sets x K x 256,
+ * pi is n_sets x K.  The library expands b to the K x 625 emission table
+ * E[:, s] = sum over the N-free symbols s marginalises (optimizer.py:182 with
+ * read_data.py:46-67) on the device.  n_sets > 1 evaluates several parameter sets
+ * over the same blocks in one launch (log-likelihood only). */
+int itr_set_model(itr_ctx *ctx, int n_sets, int K, const double *a, const double *b,
+                  const double *pi);
+
+/* Build (a, b, pi) on the GPU for n_sets parameter sets.
+ * Replaces trans_emiss_calc (get_trans_emiss.py:8-170).  params is n_sets x 9:
+ * {t_A, t_B, t_C, t_2, t_upper, t_out, N_AB, N_ABC, r} in the reference's scaled
+ * units.  cut_AB (n_int_AB+1) / cut_ABC (n_int_ABC+1, last = +inf) are normalised
+ * cutpoints shared by all sets, or NULL for the reference's "standard" quantile
+ * cutpoints (cutpoints.py:5-45).  Outputs (nullable): a n_sets x K x K,
+ * b n_sets x K x 256, pi n_sets x K, hidden K x 3 (topology, i, j) in sorted order.
+ * The model is also left installed on the device as if by itr_set_model. */
+int itr_build_model(itr_ctx *ctx, int n_sets, const double *params, int n_int_AB,
+                    int n_int_ABC, const double *cut_AB, const double *cut_ABC,
+                    double *a, double *b, double *pi, int32_t *hidden);
+/* Number of hidden states for a discretisation
+ * (get_emission_prob_mat.py:789-791). */
+int itr_num_states(int n_int_AB, int n_int_ABC);
+
+/* ---- recursions ------------------------------------------------------------------ */
+
+/* Forward log-likelihood.  Replaces loglik_wrapper / loglik_wrapper_par
+ * (optimizer.py:40-116): total[s] = sum over blocks (in block order) of
+ * forward_loglik (optimizer.py:146-162).  per_block (nullable) is n_sets x n_blocks. */
+int itr_loglik(itr_ctx *ctx, double *total, double *per_block);
+
+/* Viterbi decoding of every block with parameter set 0.  Replaces viterbi_wrapper
+ * (optimizer.py:357-377).  To be bit-exact the caller supplies the three tables
+ * whose FP64 values decide the path, computed with NumPy exactly as the reference
+ * does (optimizer.py:323-330): log_a = log(a) (K x K), log_E = log(E) (K x 625),
+ * omega0 = log(pi * E[:, V0]) per block (n_blocks x K).  path receives sum(T) state
+ * indices (uint8), blocks back to back.  path may be NULL to leave the result on the
+ * device (see itr_viterbi_fetch). */
+int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_E,
+                const double *omega0, uint8_t *path);
+int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path);
+
+/* Posterior decoding of every block with parameter set 0.  Replaces
+ * post_prob_wrapper (optimizer.py:241-262), including the reference's backward
+ * orientation (optimizer.py:210, row vector times a).  post receives sum(T) x K
+ * doubles, blocks back to back; NULL leaves the result on the device
+ * (see itr_posterior_fetch). */
+int itr_posterior(itr_ctx *ctx, double *post);
+int itr_posterior_fetch(itr_ctx *ctx, double *post);
+
+/* ---- introspection --------------------------------------------------------------- */
+
+enum itr_phase {
+    ITR_PH_LOGLIK = 0,
+    ITR_PH_VITERBI_FWD = 1,
+    ITR_PH_VITERBI_TRACE = 2,
+    ITR_PH_POST_FWD = 3,
+    ITR_PH_POST_BWD = 4,
+    ITR_PH_MODEL = 5,
+    ITR_PH_EMIT_TABLE = 6,
+    ITR_PH_COUNT = 7
+};
+/* Device time (CUDA events on the launching stream) of the most recent run of a
+ * phase, in milliseconds; negative if the phase has not run. */
+double itr_phase_ms(itr_ctx *ctx, int phase);
+/* Kernels launched by this context since creation. */
+int64_t itr_launch_count(const itr_ctx *ctx);
+int64_t itr_total_columns(const itr_ctx *ctx);
+int64_t itr_num_blocks(const itr_ctx *ctx);
+/* Fills name (NUL-terminated, <= cap bytes), SM count and compute capability. */
+int itr_device_info(itr_ctx *ctx, char *name, int cap, int *sm_count, int *cc_major,
+                    int *cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITRAILS_B200_H */

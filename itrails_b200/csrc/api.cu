@@ -1,0 +1,661 @@
+// api.cu — C ABI of libitrails_b200.so (see include/itrails_b200.h).
+//
+// Owns the device buffers (alignment blocks, padded model tables, Viterbi
+// backpointers, posterior matrix) behind an opaque context and launches the kernels
+// in hmm_kernels.cuh / model_kernels.cuh on one stream.  There is no CPU fallback:
+// if CUDA is unavailable every entry point fails with ITR_ERR_CUDA.
+#include "../../include/itrails_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "hmm_kernels.cuh"
+#include "model_build.h"
+
+using namespace itr;
+
+static thread_local std::string g_create_error;
+
+struct itr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+    int64_t launches = 0;
+
+    // blocks
+    int64_t n_blocks = 0, n_cols = 0, n_chunks = 0, max_T = 0;
+    uint16_t *d_sym = nullptr;
+    int64_t *d_off = nullptr;
+    int32_t *d_order = nullptr;
+    int64_t *d_chunk_off = nullptr;
+    int32_t *d_chunk_blk = nullptr;
+    unsigned int *d_queue = nullptr;
+    std::vector<int64_t> h_off;
+
+    // model
+    int n_sets = 0, K = 0, KP = 0;
+    double *d_A = nullptr, *d_PI = nullptr, *d_Et = nullptr;   // padded
+    double *d_braw = nullptr;                                   // n_sets x K x 256 staging
+    uint16_t *d_digits = nullptr;
+    size_t cap_A = 0, cap_PI = 0, cap_Et = 0, cap_braw = 0;
+
+    // log-likelihood
+    double *d_ll = nullptr;
+    size_t cap_ll = 0;
+    std::vector<double> h_ll;
+
+    // Viterbi
+    double *d_LA = nullptr, *d_LEt = nullptr, *d_OM0 = nullptr, *d_tmp = nullptr;
+    size_t cap_LA = 0, cap_LEt = 0, cap_OM0 = 0, cap_tmp = 0;
+    uint8_t *d_bp = nullptr, *d_comp = nullptr, *d_chunk_end = nullptr, *d_path = nullptr;
+    size_t cap_bp = 0, cap_comp = 0, cap_chunk_end = 0, cap_path = 0;
+    int32_t *d_final = nullptr;
+    size_t cap_final = 0;
+    bool have_path = false;
+
+    // posterior
+    double *d_post = nullptr;
+    size_t cap_post = 0;
+    bool have_post = false;
+
+    // timing
+    cudaEvent_t ev0[ITR_PH_COUNT]{}, ev1[ITR_PH_COUNT]{};
+    bool ev_valid[ITR_PH_COUNT]{};
+
+    ModelBuilder *builder = nullptr;
+};
+
+// ---------------------------------------------------------------------------------
+static int fail(itr_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? ITR_ERR_NOMEM : ITR_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(e_));              \
+    } while (0)
+
+template <typename T>
+static cudaError_t ensure(T *&p, size_t &cap, size_t n) {
+    if (n <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+}
+
+static void phase_begin(itr_ctx *c, int ph) { cudaEventRecord(c->ev0[ph], c->stream); }
+static void phase_end(itr_ctx *c, int ph) {
+    cudaEventRecord(c->ev1[ph], c->stream);
+    c->ev_valid[ph] = true;
+}
+
+// pad a batch of row-major matrices [nb][rows][cols] into [nb][rows_p][cols_p]
+__global__ void pad_kernel(const double *__restrict__ src, double *__restrict__ dst, int nb, int rows,
+                           int cols, int rows_p, int cols_p, double pad) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)nb * rows_p * cols_p;
+    if (idx >= total) return;
+    const int c = idx % cols_p;
+    const int r = (idx / cols_p) % rows_p;
+    const size_t b = idx / ((size_t)cols_p * rows_p);
+    dst[idx] = (r < rows && c < cols) ? src[(b * rows + r) * cols + c] : pad;
+}
+
+static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------
+extern "C" int itr_version(void) { return 1000; }
+
+extern "C" const char *itr_last_error(const itr_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int itr_create(int device, itr_ctx **out) {
+    itr_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, ITR_ERR_ARG, "itr_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, ITR_ERR_CUDA, "itr_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, ITR_ERR_ARG, "itr_create: device %d out of range [0,%d)", device, n);
+    ctx = new (std::nothrow) itr_ctx();
+    if (!ctx) return fail(nullptr, ITR_ERR_NOMEM, "itr_create: out of host memory");
+    ctx->device = device;
+    auto bail = [&](cudaError_t err, const char *what) {
+        fail(nullptr, ITR_ERR_CUDA, "itr_create: %s: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return (int)ITR_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (ctx->prop.major < 10) {
+        fail(nullptr, ITR_ERR_UNSUPPORTED, "itr_create: device %d is sm_%d%d; this library is built for sm_100a only",
+             device, ctx->prop.major, ctx->prop.minor);
+        delete ctx;
+        return ITR_ERR_UNSUPPORTED;
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (int i = 0; i < ITR_PH_COUNT; ++i) {
+        if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
+    if ((e = cudaMalloc((void **)&ctx->d_queue, sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    // symbol digit table: read_data.py:6-24 ordering
+    {
+        std::vector<uint16_t> dig(NSYM);
+        int next = 256;
+        for (int a = 0; a < 5; ++a)
+            for (int b = 0; b < 5; ++b)
+                for (int c = 0; c < 5; ++c)
+                    for (int d = 0; d < 5; ++d) {
+                        const uint16_t packed = (uint16_t)(a | (b << 3) | (c << 6) | (d << 9));
+                        if (a < 4 && b < 4 && c < 4 && d < 4) dig[64 * a + 16 * b + 4 * c + d] = packed;
+                        else dig[next++] = packed;
+                    }
+        if ((e = cudaMalloc((void **)&ctx->d_digits, NSYM * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMemcpy(ctx->d_digits, dig.data(), NSYM * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy");
+    }
+    *out = ctx;
+    return ITR_OK;
+}
+
+extern "C" void itr_destroy(itr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->builder;
+    void *ptrs[] = {ctx->d_sym, ctx->d_off, ctx->d_order, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_queue,
+                    ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
+                    ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
+                    ctx->d_path, ctx->d_final, ctx->d_post};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < ITR_PH_COUNT; ++i) {
+        if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
+        if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int itr_device_info(itr_ctx *ctx, char *name, int cap, int *sm_count, int *cc_major, int *cc_minor) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (name && cap > 0) {
+        strncpy(name, ctx->prop.name, cap - 1);
+        name[cap - 1] = 0;
+    }
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    return ITR_OK;
+}
+
+extern "C" double itr_phase_ms(itr_ctx *ctx, int phase) {
+    if (!ctx || phase < 0 || phase >= ITR_PH_COUNT || !ctx->ev_valid[phase]) return -1.0;
+    cudaSetDevice(ctx->device);
+    if (cudaEventSynchronize(ctx->ev1[phase]) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0[phase], ctx->ev1[phase]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+extern "C" int64_t itr_launch_count(const itr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t itr_total_columns(const itr_ctx *ctx) { return ctx ? ctx->n_cols : 0; }
+extern "C" int64_t itr_num_blocks(const itr_ctx *ctx) { return ctx ? ctx->n_blocks : 0; }
+
+// ---------------------------------------------------------------------------------
+// blocks
+// ---------------------------------------------------------------------------------
+static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off, int64_t n_blocks) {
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n_cols = off[n_blocks];
+    std::vector<int32_t> order(n_blocks);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return off[x + 1] - off[x] > off[y + 1] - off[y];
+    });
+    std::vector<int64_t> chunk_off(n_blocks + 1, 0);
+    int64_t max_T = 0;
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const int64_t T = off[b + 1] - off[b];
+        max_T = std::max(max_T, T);
+        chunk_off[b + 1] = chunk_off[b] + (T + VCHUNK - 1) / VCHUNK;
+    }
+    const int64_t n_chunks = chunk_off[n_blocks];
+    std::vector<int32_t> chunk_blk(n_chunks);
+    for (int64_t b = 0; b < n_blocks; ++b)
+        std::fill(chunk_blk.begin() + chunk_off[b], chunk_blk.begin() + chunk_off[b + 1], (int32_t)b);
+
+    for (void **p : {(void **)&ctx->d_sym, (void **)&ctx->d_off, (void **)&ctx->d_order,
+                     (void **)&ctx->d_chunk_off, (void **)&ctx->d_chunk_blk}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    ctx->n_blocks = ctx->n_cols = ctx->n_chunks = 0;
+    ctx->have_path = ctx->have_post = false;
+    // +64 columns of slack so tile prefetches past the end stay in bounds
+    CK(cudaMalloc((void **)&ctx->d_sym, (size_t)(n_cols + 64) * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&ctx->d_off, (size_t)(n_blocks + 1) * sizeof(int64_t)));
+    CK(cudaMalloc((void **)&ctx->d_order, (size_t)n_blocks * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&ctx->d_chunk_off, (size_t)(n_blocks + 1) * sizeof(int64_t)));
+    CK(cudaMalloc((void **)&ctx->d_chunk_blk, (size_t)std::max<int64_t>(n_chunks, 1) * sizeof(int32_t)));
+    CK(cudaMemsetAsync(ctx->d_sym + n_cols, 0, 64 * sizeof(uint16_t), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sym, sym, (size_t)n_cols * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)n_blocks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_chunk_off, chunk_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_chunk_blk, chunk_blk.data(), (size_t)n_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_off.assign(off, off + n_blocks + 1);
+    ctx->n_blocks = n_blocks;
+    ctx->n_cols = n_cols;
+    ctx->n_chunks = n_chunks;
+    ctx->max_T = max_T;
+    return ITR_OK;
+}
+
+static int check_offsets(itr_ctx *ctx, const int64_t *off, int64_t n_blocks) {
+    if (!off) return fail(ctx, ITR_ERR_ARG, "block_offsets is NULL");
+    if (n_blocks <= 0) return fail(ctx, ITR_ERR_ARG, "n_blocks must be positive (got %lld)", (long long)n_blocks);
+    if (n_blocks > 0x7fffffff / 2) return fail(ctx, ITR_ERR_ARG, "too many blocks (%lld)", (long long)n_blocks);
+    if (off[0] != 0) return fail(ctx, ITR_ERR_ARG, "block_offsets[0] must be 0");
+    for (int64_t b = 0; b < n_blocks; ++b)
+        if (off[b + 1] <= off[b])
+            return fail(ctx, ITR_ERR_ARG, "block %lld is empty or offsets are not increasing", (long long)b);
+    return ITR_OK;
+}
+
+extern "C" int itr_load_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off, int64_t n_blocks) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!sym) return fail(ctx, ITR_ERR_ARG, "sym is NULL");
+    int rc = check_offsets(ctx, off, n_blocks);
+    if (rc) return rc;
+    const int64_t n = off[n_blocks];
+    for (int64_t i = 0; i < n; ++i)
+        if (sym[i] >= NSYM) return fail(ctx, ITR_ERR_ARG, "symbol %u at column %lld is outside 0..624", sym[i], (long long)i);
+    return install_blocks(ctx, sym, off, n_blocks);
+}
+
+extern "C" int itr_load_blocks_i64(itr_ctx *ctx, const int64_t *sym, const int64_t *off, int64_t n_blocks) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!sym) return fail(ctx, ITR_ERR_ARG, "sym is NULL");
+    int rc = check_offsets(ctx, off, n_blocks);
+    if (rc) return rc;
+    const int64_t n = off[n_blocks];
+    std::vector<uint16_t> tmp;
+    try { tmp.resize(n); } catch (...) { return fail(ctx, ITR_ERR_NOMEM, "out of host memory"); }
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = sym[i];
+        if (v < 0 || v >= NSYM) return fail(ctx, ITR_ERR_ARG, "symbol %lld at column %lld is outside 0..624", (long long)v, (long long)i);
+        tmp[i] = (uint16_t)v;
+    }
+    return install_blocks(ctx, tmp.data(), off, n_blocks);
+}
+
+// ---------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------
+static int padded_K(int K) { return ((K + 31) / 32) * 32; }
+
+// Installs a model whose raw arrays are already on the device.
+int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, const double *d_b, const double *d_pi) {
+    const int KP = padded_K(K);
+    CK(ensure(ctx->d_A, ctx->cap_A, (size_t)n_sets * KP * KP));
+    CK(ensure(ctx->d_PI, ctx->cap_PI, (size_t)n_sets * KP));
+    CK(ensure(ctx->d_Et, ctx->cap_Et, (size_t)n_sets * NSYM * KP));
+    phase_begin(ctx, ITR_PH_EMIT_TABLE);
+    pad_kernel<<<blocks_for((size_t)n_sets * KP * KP, 256), 256, 0, ctx->stream>>>(d_a, ctx->d_A, n_sets, K, K, KP, KP, 0.0);
+    pad_kernel<<<blocks_for((size_t)n_sets * KP, 256), 256, 0, ctx->stream>>>(d_pi, ctx->d_PI, n_sets, 1, K, 1, KP, 0.0);
+    emission_table_kernel<<<blocks_for((size_t)n_sets * NSYM * KP, 256), 256, 0, ctx->stream>>>(d_b, ctx->d_digits, ctx->d_Et, K, KP, n_sets);
+    phase_end(ctx, ITR_PH_EMIT_TABLE);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    ctx->n_sets = n_sets;
+    ctx->K = K;
+    ctx->KP = KP;
+    ctx->have_path = ctx->have_post = false;
+    return ITR_OK;
+}
+
+extern "C" int itr_set_model(itr_ctx *ctx, int n_sets, int K, const double *a, const double *b, const double *pi) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!a || !b || !pi) return fail(ctx, ITR_ERR_ARG, "itr_set_model: a, b and pi must be non-NULL");
+    if (n_sets < 1) return fail(ctx, ITR_ERR_ARG, "itr_set_model: n_sets must be >= 1");
+    if (K < 1 || K > ITR_MAX_STATES) return fail(ctx, ITR_ERR_ARG, "itr_set_model: K=%d outside 1..%d", K, ITR_MAX_STATES);
+    CK(cudaSetDevice(ctx->device));
+    const size_t na = (size_t)n_sets * K * K, nb = (size_t)n_sets * K * 256, np = (size_t)n_sets * K;
+    CK(ensure(ctx->d_braw, ctx->cap_braw, na + nb + np));
+    double *d_a = ctx->d_braw, *d_b = d_a + na, *d_pi = d_b + nb;
+    CK(cudaMemcpyAsync(d_a, a, na * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_b, b, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_pi, pi, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = install_model_device(ctx, n_sets, K, d_a, d_b, d_pi);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ITR_OK;
+}
+
+extern "C" int itr_num_states(int n_int_AB, int n_int_ABC) {
+    if (n_int_AB < 1 || n_int_ABC < 1) return -1;
+    return n_int_AB * n_int_ABC + 3 * n_int_ABC + 3 * (n_int_ABC * (n_int_ABC - 1) / 2);
+}
+
+extern "C" int itr_build_model(itr_ctx *ctx, int n_sets, const double *params, int n_int_AB, int n_int_ABC,
+                               const double *cut_AB, const double *cut_ABC, double *a, double *b, double *pi,
+                               int32_t *hidden) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!params) return fail(ctx, ITR_ERR_ARG, "itr_build_model: params is NULL");
+    if (n_sets < 1) return fail(ctx, ITR_ERR_ARG, "itr_build_model: n_sets must be >= 1");
+    if (n_int_AB < 1 || n_int_ABC < 1) return fail(ctx, ITR_ERR_ARG, "itr_build_model: n_int_AB and n_int_ABC must be >= 1");
+    const int K = itr_num_states(n_int_AB, n_int_ABC);
+    if (K > ITR_MAX_STATES) return fail(ctx, ITR_ERR_UNSUPPORTED, "itr_build_model: K=%d exceeds %d", K, ITR_MAX_STATES);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->builder) ctx->builder = new (std::nothrow) ModelBuilder();
+    if (!ctx->builder) return fail(ctx, ITR_ERR_NOMEM, "out of host memory");
+    std::string msg;
+    phase_begin(ctx, ITR_PH_MODEL);
+    const double *d_a = nullptr, *d_b = nullptr, *d_pi = nullptr;
+    int64_t launched = 0;
+    int rc = ctx->builder->build(ctx->stream, n_sets, params, n_int_AB, n_int_ABC, cut_AB, cut_ABC, &d_a, &d_b, &d_pi,
+                                 hidden, &launched, msg);
+    phase_end(ctx, ITR_PH_MODEL);
+    ctx->launches += launched;
+    if (rc) return fail(ctx, rc, "itr_build_model: %s", msg.c_str());
+    if (a) CK(cudaMemcpyAsync(a, d_a, (size_t)n_sets * K * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(b, d_b, (size_t)n_sets * K * 256 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pi) CK(cudaMemcpyAsync(pi, d_pi, (size_t)n_sets * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = install_model_device(ctx, n_sets, K, d_a, d_b, d_pi);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ITR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// launch geometry: one warp per chain; spread chains over SMs before stacking warps.
+// ---------------------------------------------------------------------------------
+struct Geometry {
+    int warps, grid;
+};
+static Geometry geometry(const itr_ctx *ctx, int64_t n_chains, int max_warps_per_sm) {
+    const int sms = ctx->prop.multiProcessorCount;
+    int w = (int)std::min<int64_t>(8, std::max<int64_t>(1, (n_chains + sms - 1) / sms));
+    const int64_t want = (n_chains + w - 1) / w;
+    const int64_t cap = (int64_t)sms * std::max(1, max_warps_per_sm / w);
+    return {w, (int)std::max<int64_t>(1, std::min(want, cap))};
+}
+
+static ChainSet chain_set(const itr_ctx *ctx, int n_sets) {
+    return ChainSet{ctx->d_sym, ctx->d_off, ctx->d_order, (int32_t)ctx->n_blocks, n_sets, ctx->d_queue};
+}
+
+template <int MODE>
+static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha) {
+    const int K = ctx->K, KP = ctx->KP;
+    const Geometry g = geometry(ctx, (int64_t)n_sets * ctx->n_blocks, 16);
+    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+    const ChainSet cs = chain_set(ctx, n_sets);
+    cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream);
+#define FWD_REG(KT)                                                                               \
+    forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, \
+                                                                                 ctx->d_Et, K, KP, d_ll, d_alpha)
+#define FWD_GEN(NS)                                                                               \
+    forward_kernel<4, NS, false, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, \
+                                                                                  ctx->d_Et, K, KP, d_ll, d_alpha)
+    if (K <= 32) {
+        switch ((K + 3) / 4) {
+            case 1: FWD_REG(4); break;
+            case 2: FWD_REG(8); break;
+            case 3: FWD_REG(12); break;
+            case 4: FWD_REG(16); break;
+            case 5: FWD_REG(20); break;
+            case 6: FWD_REG(24); break;
+            case 7: FWD_REG(28); break;
+            default: FWD_REG(32); break;
+        }
+    } else {
+        switch (KP / 32) {
+            case 2: FWD_GEN(2); break;
+            case 3: FWD_GEN(3); break;
+            case 4: FWD_GEN(4); break;
+            case 5: FWD_GEN(5); break;
+            case 6: FWD_GEN(6); break;
+            case 7: FWD_GEN(7); break;
+            default: FWD_GEN(8); break;
+        }
+    }
+#undef FWD_REG
+#undef FWD_GEN
+    ctx->launches += 1;
+}
+
+static void launch_backward(itr_ctx *ctx) {
+    const int K = ctx->K, KP = ctx->KP;
+    const Geometry g = geometry(ctx, ctx->n_blocks, 16);
+    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+    const ChainSet cs = chain_set(ctx, 1);
+    cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream);
+#define BWD_REG(KT) \
+    backward_posterior_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_Et, K, KP, ctx->d_post)
+#define BWD_GEN(NS) \
+    backward_posterior_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_Et, K, KP, ctx->d_post)
+    if (K <= 32) {
+        switch ((K + 3) / 4) {
+            case 1: BWD_REG(4); break;
+            case 2: BWD_REG(8); break;
+            case 3: BWD_REG(12); break;
+            case 4: BWD_REG(16); break;
+            case 5: BWD_REG(20); break;
+            case 6: BWD_REG(24); break;
+            case 7: BWD_REG(28); break;
+            default: BWD_REG(32); break;
+        }
+    } else {
+        switch (KP / 32) {
+            case 2: BWD_GEN(2); break;
+            case 3: BWD_GEN(3); break;
+            case 4: BWD_GEN(4); break;
+            case 5: BWD_GEN(5); break;
+            case 6: BWD_GEN(6); break;
+            case 7: BWD_GEN(7); break;
+            default: BWD_GEN(8); break;
+        }
+    }
+#undef BWD_REG
+#undef BWD_GEN
+    ctx->launches += 1;
+}
+
+static void launch_viterbi_forward(itr_ctx *ctx) {
+    const int K = ctx->K, KP = ctx->KP;
+    const Geometry g = geometry(ctx, ctx->n_blocks, 16);
+    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+    const ChainSet cs = chain_set(ctx, 1);
+    cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream);
+#define VIT_REG(KT)                                                                                  \
+    viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, ctx->stream>>>(                  \
+        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, KP, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
+#define VIT_GEN(NS)                                                                                  \
+    viterbi_forward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, ctx->stream>>>(                 \
+        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, KP, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
+    if (K <= 32) {
+        switch ((K + 3) / 4) {
+            case 1: VIT_REG(4); break;
+            case 2: VIT_REG(8); break;
+            case 3: VIT_REG(12); break;
+            case 4: VIT_REG(16); break;
+            case 5: VIT_REG(20); break;
+            case 6: VIT_REG(24); break;
+            case 7: VIT_REG(28); break;
+            default: VIT_REG(32); break;
+        }
+    } else {
+        switch (KP / 32) {
+            case 2: VIT_GEN(2); break;
+            case 3: VIT_GEN(3); break;
+            case 4: VIT_GEN(4); break;
+            case 5: VIT_GEN(5); break;
+            case 6: VIT_GEN(6); break;
+            case 7: VIT_GEN(7); break;
+            default: VIT_GEN(8); break;
+        }
+    }
+#undef VIT_REG
+#undef VIT_GEN
+    ctx->launches += 1;
+}
+
+static int need_ready(itr_ctx *ctx, const char *who) {
+    if (ctx->n_blocks == 0) return fail(ctx, ITR_ERR_STATE, "%s: no blocks loaded (call itr_load_blocks first)", who);
+    if (ctx->K == 0) return fail(ctx, ITR_ERR_STATE, "%s: no model installed (call itr_set_model or itr_build_model first)", who);
+    return ITR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// forward log-likelihood
+// ---------------------------------------------------------------------------------
+extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
+    if (!ctx) return ITR_ERR_ARG;
+    int rc = need_ready(ctx, "itr_loglik");
+    if (rc) return rc;
+    if (!total && !per_block) return fail(ctx, ITR_ERR_ARG, "itr_loglik: total and per_block are both NULL");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->n_sets * ctx->n_blocks;
+    CK(ensure(ctx->d_ll, ctx->cap_ll, n));
+    phase_begin(ctx, ITR_PH_LOGLIK);
+    launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr);
+    phase_end(ctx, ITR_PH_LOGLIK);
+    CK(cudaGetLastError());
+    ctx->h_ll.resize(n);
+    CK(cudaMemcpyAsync(ctx->h_ll.data(), ctx->d_ll, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (per_block) memcpy(per_block, ctx->h_ll.data(), n * sizeof(double));
+    if (total) {
+        // the reference accumulates block results in block order (optimizer.py:112-113)
+        for (int s = 0; s < ctx->n_sets; ++s) {
+            double acc = 0.0;
+            const double *p = ctx->h_ll.data() + (size_t)s * ctx->n_blocks;
+            for (int64_t b = 0; b < ctx->n_blocks; ++b) acc += p[b];
+            total[s] = acc;
+        }
+    }
+    return ITR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Viterbi
+// ---------------------------------------------------------------------------------
+extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_E, const double *omega0,
+                           uint8_t *path) {
+    if (!ctx) return ITR_ERR_ARG;
+    int rc = need_ready(ctx, "itr_viterbi");
+    if (rc) return rc;
+    if (!log_a || !log_E || !omega0) return fail(ctx, ITR_ERR_ARG, "itr_viterbi: log_a, log_E and omega0 must be non-NULL");
+    CK(cudaSetDevice(ctx->device));
+    const int K = ctx->K, KP = ctx->KP;
+    const int64_t nb = ctx->n_blocks;
+    const double ninf = -std::numeric_limits<double>::infinity();
+    CK(ensure(ctx->d_LA, ctx->cap_LA, (size_t)KP * KP));
+    CK(ensure(ctx->d_LEt, ctx->cap_LEt, (size_t)NSYM * KP));
+    CK(ensure(ctx->d_OM0, ctx->cap_OM0, (size_t)nb * KP));
+    const size_t ntmp = std::max<size_t>((size_t)K * NSYM, (size_t)nb * K) + (size_t)K * K;
+    CK(ensure(ctx->d_tmp, ctx->cap_tmp, ntmp));
+    CK(ensure(ctx->d_bp, ctx->cap_bp, (size_t)(ctx->n_cols + 1) * KP));
+    CK(ensure(ctx->d_comp, ctx->cap_comp, (size_t)(ctx->n_chunks + 1) * KP));
+    CK(ensure(ctx->d_chunk_end, ctx->cap_chunk_end, (size_t)ctx->n_chunks + 1));
+    CK(ensure(ctx->d_path, ctx->cap_path, (size_t)ctx->n_cols));
+    CK(ensure(ctx->d_final, ctx->cap_final, (size_t)nb));
+    double *t_la = ctx->d_tmp, *t_big = ctx->d_tmp + (size_t)K * K;
+    CK(cudaMemcpyAsync(t_la, log_a, (size_t)K * K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    pad_kernel<<<blocks_for((size_t)KP * KP, 256), 256, 0, ctx->stream>>>(t_la, ctx->d_LA, 1, K, K, KP, KP, ninf);
+    CK(cudaMemcpyAsync(t_big, log_E, (size_t)K * NSYM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    transpose_table_kernel<<<blocks_for((size_t)NSYM * KP, 256), 256, 0, ctx->stream>>>(t_big, ctx->d_LEt, K, KP, 0.0);
+    CK(cudaMemcpyAsync(t_big, omega0, (size_t)nb * K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    pad_kernel<<<blocks_for((size_t)nb * KP, 256), 256, 0, ctx->stream>>>(t_big, ctx->d_OM0, (int)nb, 1, K, 1, KP, ninf);
+    ctx->launches += 3;
+    phase_begin(ctx, ITR_PH_VITERBI_FWD);
+    launch_viterbi_forward(ctx);
+    phase_end(ctx, ITR_PH_VITERBI_FWD);
+    phase_begin(ctx, ITR_PH_VITERBI_TRACE);
+    viterbi_boundary_kernel<<<blocks_for((size_t)nb, 128), 128, 0, ctx->stream>>>(ctx->d_off, ctx->d_chunk_off, ctx->d_comp,
+                                                                                ctx->d_final, KP, (int)nb, ctx->d_chunk_end);
+    viterbi_traceback_kernel<<<blocks_for((size_t)ctx->n_chunks, 128), 128, 0, ctx->stream>>>(
+        ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, ctx->d_chunk_end, KP, ctx->n_chunks, ctx->d_path);
+    phase_end(ctx, ITR_PH_VITERBI_TRACE);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    ctx->have_path = true;
+    if (path) CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ITR_OK;
+}
+
+extern "C" int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!path) return fail(ctx, ITR_ERR_ARG, "itr_viterbi_fetch: path is NULL");
+    if (!ctx->have_path) return fail(ctx, ITR_ERR_STATE, "itr_viterbi_fetch: no Viterbi result on the device");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ITR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// posterior
+// ---------------------------------------------------------------------------------
+extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
+    if (!ctx) return ITR_ERR_ARG;
+    int rc = need_ready(ctx, "itr_posterior");
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->n_cols * ctx->K;
+    CK(ensure(ctx->d_post, ctx->cap_post, n));
+    phase_begin(ctx, ITR_PH_POST_FWD);
+    launch_forward<1>(ctx, 1, nullptr, ctx->d_post);
+    phase_end(ctx, ITR_PH_POST_FWD);
+    phase_begin(ctx, ITR_PH_POST_BWD);
+    launch_backward(ctx);
+    phase_end(ctx, ITR_PH_POST_BWD);
+    CK(cudaGetLastError());
+    ctx->have_post = true;
+    if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ITR_OK;
+}
+
+extern "C" int itr_posterior_fetch(itr_ctx *ctx, double *post) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!post) return fail(ctx, ITR_ERR_ARG, "itr_posterior_fetch: post is NULL");
+    if (!ctx->have_post) return fail(ctx, ITR_ERR_STATE, "itr_posterior_fetch: no posterior on the device");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(post, ctx->d_post, (size_t)ctx->n_cols * ctx->K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ITR_OK;
+}

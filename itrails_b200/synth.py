@@ -1,0 +1,70 @@
+"""Deterministic synthetic alignments of the shapes BASELINE.json names: columns are
+sampled from the HMM itself (dwell-time sampling of the hidden path, then emitted
+columns), and with probability ``p_n`` per column one random species is overwritten
+by ``N`` so that symbols 256..624 occur."""
+from __future__ import annotations
+
+import numpy as np
+
+from .read_data import _build_tables, get_obs_state_dct  # noqa: F401
+
+
+def sample_block(a, b, pi, T, rng, p_n=0.01):
+    """One block of ``T`` columns as int64 symbol indices (like maf_parser's output)."""
+    from . import read_data as rd
+    if rd._CODE_TO_INDEX is None:
+        rd._build_tables()
+    K = a.shape[0]
+    stay = np.clip(np.diag(a), 0.0, 1.0 - 1e-12)
+    off = np.array(a, dtype=np.float64)
+    np.fill_diagonal(off, 0.0)
+    off /= off.sum(1, keepdims=True)
+    bc = np.cumsum(b / b.sum(1, keepdims=True), axis=1)
+    z = rng.choice(K, p=pi / pi.sum())
+    V = np.empty(T, dtype=np.int64)
+    t = 0
+    while t < T:
+        d = min(int(rng.geometric(1.0 - stay[z])), T - t)
+        V[t:t + d] = np.minimum(np.searchsorted(bc[z], rng.random(d)), 255)
+        t += d
+        z = rng.choice(K, p=off[z])
+    hit = np.nonzero(rng.random(T) < p_n)[0]
+    if len(hit):
+        sp = rng.integers(0, 4, size=len(hit))
+        v = V[hit]
+        digits = np.stack([(v >> 6) & 3, (v >> 4) & 3, (v >> 2) & 3, v & 3], axis=1)
+        digits[np.arange(len(hit)), sp] = 4
+        code = ((digits[:, 0] * 5 + digits[:, 1]) * 5 + digits[:, 2]) * 5 + digits[:, 3]
+        V[hit] = rd._CODE_TO_INDEX[code]
+    return V
+
+
+def block_lengths(n_blocks, total, rng, lo=50_000, hi=150_000):
+    """``n_blocks`` lengths ~ uniform[lo, hi], rescaled so that they sum to ``total``."""
+    raw = rng.uniform(lo, hi, size=n_blocks)
+    lens = np.maximum(1, np.floor(raw * (total / raw.sum()))).astype(np.int64)
+    lens[-1] += total - lens.sum()
+    if lens[-1] < 1:
+        raise ValueError("total too small for the number of blocks")
+    return lens
+
+
+def alignment(a, b, pi, lengths, seed, p_n=0.01):
+    rng = np.random.default_rng(seed)
+    return [sample_block(a, b, pi, int(T), rng, p_n) for T in lengths]
+
+
+EXAMPLE_PARAMS = dict(mu=1e-8, N_AB=50000.0, N_ABC=50000.0, t_1=240000.0, t_2=40000.0,
+                      t_upper=745069.3855, r=1e-8)
+
+
+def example_model_args(n_int_ABC=3, p=None):
+    """The nine scaled scalars of trans_emiss_calc for examples/example_config.yaml's
+    starting values (scaling: workflow_optimize.py:369-405; t_out: optimizer.py:525-541)."""
+    p = dict(EXAMPLE_PARAMS if p is None else p)
+    mu = p["mu"]
+    N_AB, N_ABC = p["N_AB"] * mu, p["N_ABC"] * mu
+    t_1, t_2, t_upper, r = p["t_1"] * mu, p["t_2"] * mu, p["t_upper"] * mu, p["r"] / mu
+    cut_last = -np.log1p(-(n_int_ABC - 1) / n_int_ABC)
+    t_out = t_1 + t_2 + cut_last * N_ABC + t_upper + 2 * N_ABC
+    return np.array([t_1, t_1, t_1 + t_2, t_2, t_upper, t_out, N_AB, N_ABC, r])
