@@ -131,7 +131,9 @@ enum itr_phase {
     ITR_PH_POST_BWD = 4,
     ITR_PH_MODEL = 5,
     ITR_PH_EMIT_TABLE = 6,
-    ITR_PH_COUNT = 7
+    ITR_PH_POST_COMBINE = 7,
+    ITR_PH_POST_TOTAL = 8,   /* forward || backward, then combine (wall on the device) */
+    ITR_PH_COUNT = 9
 };
 /* Device time (CUDA events on the launching stream) of the most recent run of a
  * phase, in milliseconds; negative if the phase has not run. */

@@ -24,7 +24,7 @@ class ItrailsCudaError(ItrailsError):
 
 ITR_ERR_ARG, ITR_ERR_STATE, ITR_ERR_CUDA, ITR_ERR_NOMEM, ITR_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 PHASES = {"loglik": 0, "viterbi_fwd": 1, "viterbi_trace": 2, "post_fwd": 3, "post_bwd": 4,
-          "model": 5, "emit_table": 6}
+          "model": 5, "emit_table": 6, "post_combine": 7, "post_total": 8}
 
 _c_ctx = ctypes.c_void_p
 _dp = ctypes.POINTER(ctypes.c_double)

@@ -28,7 +28,8 @@ static thread_local std::string g_create_error;
 
 struct itr_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaDeviceProp prop{};
     std::string err;
     int64_t launches = 0;
@@ -65,8 +66,8 @@ struct itr_ctx {
     bool have_path = false;
 
     // posterior
-    double *d_post = nullptr;
-    size_t cap_post = 0;
+    double *d_post = nullptr, *d_beta = nullptr;
+    size_t cap_post = 0, cap_beta = 0;
     bool have_post = false;
 
     // timing
@@ -106,9 +107,9 @@ static cudaError_t ensure(T *&p, size_t &cap, size_t n) {
     return e;
 }
 
-static void phase_begin(itr_ctx *c, int ph) { cudaEventRecord(c->ev0[ph], c->stream); }
-static void phase_end(itr_ctx *c, int ph) {
-    cudaEventRecord(c->ev1[ph], c->stream);
+static void phase_begin(itr_ctx *c, int ph, cudaStream_t st = nullptr) { cudaEventRecord(c->ev0[ph], st ? st : c->stream); }
+static void phase_end(itr_ctx *c, int ph, cudaStream_t st = nullptr) {
+    cudaEventRecord(c->ev1[ph], st ? st : c->stream);
     c->ev_valid[ph] = true;
 }
 
@@ -162,11 +163,14 @@ extern "C" int itr_create(int device, itr_ctx **out) {
         return ITR_ERR_UNSUPPORTED;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
         if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
         if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
-    if ((e = cudaMalloc((void **)&ctx->d_queue, sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_queue, 4 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
     // symbol digit table: read_data.py:6-24 ordering
     {
         std::vector<uint16_t> dig(NSYM);
@@ -191,17 +195,21 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     delete ctx->builder;
     void *ptrs[] = {ctx->d_sym, ctx->d_off, ctx->d_order, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_queue,
                     ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
-                    ctx->d_path, ctx->d_final, ctx->d_post};
+                    ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
     }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -412,121 +420,106 @@ static Geometry geometry(const itr_ctx *ctx, int64_t n_chains, int max_warps_per
     return {w, (int)std::max<int64_t>(1, std::min(want, cap))};
 }
 
-static ChainSet chain_set(const itr_ctx *ctx, int n_sets) {
-    return ChainSet{ctx->d_sym, ctx->d_off, ctx->d_order, (int32_t)ctx->n_blocks, n_sets, ctx->d_queue};
+static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
+    return ChainSet{ctx->d_sym, ctx->d_off, ctx->d_order, (int32_t)ctx->n_blocks, n_sets, ctx->d_queue + slot};
 }
+
+// K <= 32: columns in registers, KT = K rounded up to 4.  K > 32: NS = ceil(K/32)
+// states per lane, columns streamed.
+#ifdef ITR_FAST_BUILD   /* experiments only: K in 25..32 and 65..96 */
+#define ITR_DISPATCH_K(K, REG, GEN)     \
+    do {                                \
+        if ((K) <= 28) REG(28);         \
+        else if ((K) <= 32) REG(32);    \
+        else GEN(3);                    \
+    } while (0)
+#else
+#define ITR_DISPATCH_K(K, REG, GEN)     \
+    do {                                \
+        if ((K) <= 32) {                \
+            switch (((K) + 3) / 4) {    \
+                case 1: REG(4); break;  \
+                case 2: REG(8); break;  \
+                case 3: REG(12); break; \
+                case 4: REG(16); break; \
+                case 5: REG(20); break; \
+                case 6: REG(24); break; \
+                case 7: REG(28); break; \
+                default: REG(32); break;\
+            }                           \
+        } else {                        \
+            switch (((K) + 31) / 32) {  \
+                case 2: GEN(2); break;  \
+                case 3: GEN(3); break;  \
+                case 4: GEN(4); break;  \
+                case 5: GEN(5); break;  \
+                case 6: GEN(6); break;  \
+                case 7: GEN(7); break;  \
+                default: GEN(8); break; \
+            }                           \
+        }                               \
+    } while (0)
+#endif
 
 template <int MODE>
 static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha) {
     const int K = ctx->K, KP = ctx->KP;
     const Geometry g = geometry(ctx, (int64_t)n_sets * ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    const ChainSet cs = chain_set(ctx, n_sets);
-    cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream);
-#define FWD_REG(KT)                                                                               \
-    forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, \
-                                                                                 ctx->d_Et, K, KP, d_ll, d_alpha)
-#define FWD_GEN(NS)                                                                               \
-    forward_kernel<4, NS, false, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, \
-                                                                                  ctx->d_Et, K, KP, d_ll, d_alpha)
-    if (K <= 32) {
-        switch ((K + 3) / 4) {
-            case 1: FWD_REG(4); break;
-            case 2: FWD_REG(8); break;
-            case 3: FWD_REG(12); break;
-            case 4: FWD_REG(16); break;
-            case 5: FWD_REG(20); break;
-            case 6: FWD_REG(24); break;
-            case 7: FWD_REG(28); break;
-            default: FWD_REG(32); break;
-        }
-    } else {
-        switch (KP / 32) {
-            case 2: FWD_GEN(2); break;
-            case 3: FWD_GEN(3); break;
-            case 4: FWD_GEN(4); break;
-            case 5: FWD_GEN(5); break;
-            case 6: FWD_GEN(6); break;
-            case 7: FWD_GEN(7); break;
-            default: FWD_GEN(8); break;
-        }
-    }
+    const ChainSet cs = chain_set(ctx, n_sets, 0);
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), ctx->stream);
+#define FWD_REG(KT) \
+    forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
+#define FWD_GEN(NS) \
+    forward_kernel<4, NS, false, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
+    ITR_DISPATCH_K(K, FWD_REG, FWD_GEN);
 #undef FWD_REG
 #undef FWD_GEN
     ctx->launches += 1;
 }
 
-static void launch_backward(itr_ctx *ctx) {
+static void launch_backward(itr_ctx *ctx, cudaStream_t st) {
     const int K = ctx->K, KP = ctx->KP;
     const Geometry g = geometry(ctx, ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    const ChainSet cs = chain_set(ctx, 1);
-    cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream);
-#define BWD_REG(KT) \
-    backward_posterior_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_Et, K, KP, ctx->d_post)
-#define BWD_GEN(NS) \
-    backward_posterior_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_Et, K, KP, ctx->d_post)
-    if (K <= 32) {
-        switch ((K + 3) / 4) {
-            case 1: BWD_REG(4); break;
-            case 2: BWD_REG(8); break;
-            case 3: BWD_REG(12); break;
-            case 4: BWD_REG(16); break;
-            case 5: BWD_REG(20); break;
-            case 6: BWD_REG(24); break;
-            case 7: BWD_REG(28); break;
-            default: BWD_REG(32); break;
-        }
-    } else {
-        switch (KP / 32) {
-            case 2: BWD_GEN(2); break;
-            case 3: BWD_GEN(3); break;
-            case 4: BWD_GEN(4); break;
-            case 5: BWD_GEN(5); break;
-            case 6: BWD_GEN(6); break;
-            case 7: BWD_GEN(7); break;
-            default: BWD_GEN(8); break;
-        }
-    }
+    const ChainSet cs = chain_set(ctx, 1, 1);
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+#define BWD_REG(KT) backward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_Et, K, ctx->d_beta)
+#define BWD_GEN(NS) backward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_Et, K, ctx->d_beta)
+    ITR_DISPATCH_K(K, BWD_REG, BWD_GEN);
 #undef BWD_REG
 #undef BWD_GEN
     ctx->launches += 1;
+}
+
+template <int COLS>
+static cudaError_t launch_combine_t(itr_ctx *ctx) {
+    const size_t sh = (size_t)COLS * ctx->K * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(posterior_combine_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    posterior_combine_kernel<COLS><<<blocks_for((size_t)ctx->n_cols, COLS), COLS, sh, ctx->stream>>>(ctx->d_post, ctx->d_beta, ctx->K, ctx->n_cols);
+    ctx->launches += 1;
+    return cudaSuccess;
+}
+static cudaError_t launch_combine(itr_ctx *ctx) {
+    if (ctx->K <= 40) return launch_combine_t<256>(ctx);
+    if (ctx->K <= 160) return launch_combine_t<64>(ctx);
+    return launch_combine_t<32>(ctx);
 }
 
 static void launch_viterbi_forward(itr_ctx *ctx) {
     const int K = ctx->K, KP = ctx->KP;
     const Geometry g = geometry(ctx, ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    const ChainSet cs = chain_set(ctx, 1);
-    cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream);
-#define VIT_REG(KT)                                                                                  \
-    viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, ctx->stream>>>(                  \
-        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, KP, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
-#define VIT_GEN(NS)                                                                                  \
-    viterbi_forward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, ctx->stream>>>(                 \
-        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, KP, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
-    if (K <= 32) {
-        switch ((K + 3) / 4) {
-            case 1: VIT_REG(4); break;
-            case 2: VIT_REG(8); break;
-            case 3: VIT_REG(12); break;
-            case 4: VIT_REG(16); break;
-            case 5: VIT_REG(20); break;
-            case 6: VIT_REG(24); break;
-            case 7: VIT_REG(28); break;
-            default: VIT_REG(32); break;
-        }
-    } else {
-        switch (KP / 32) {
-            case 2: VIT_GEN(2); break;
-            case 3: VIT_GEN(3); break;
-            case 4: VIT_GEN(4); break;
-            case 5: VIT_GEN(5); break;
-            case 6: VIT_GEN(6); break;
-            case 7: VIT_GEN(7); break;
-            default: VIT_GEN(8); break;
-        }
-    }
+    const ChainSet cs = chain_set(ctx, 1, 2);
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), ctx->stream);
+#define VIT_REG(KT)                                                                 \
+    viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, ctx->stream>>>( \
+        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
+#define VIT_GEN(NS)                                                                  \
+    viterbi_forward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, ctx->stream>>>( \
+        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
+    ITR_DISPATCH_K(K, VIT_REG, VIT_GEN);
 #undef VIT_REG
 #undef VIT_GEN
     ctx->launches += 1;
@@ -637,12 +630,24 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->n_cols * ctx->K;
     CK(ensure(ctx->d_post, ctx->cap_post, n));
+    CK(ensure(ctx->d_beta, ctx->cap_beta, n));
+    // forward (alpha -> d_post) on the main stream, backward (beta -> d_beta) on the
+    // second stream, concurrently; then the combine on the main stream.
+    phase_begin(ctx, ITR_PH_POST_TOTAL);
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    phase_begin(ctx, ITR_PH_POST_BWD, ctx->stream2);
+    launch_backward(ctx, ctx->stream2);
+    phase_end(ctx, ITR_PH_POST_BWD, ctx->stream2);
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     phase_begin(ctx, ITR_PH_POST_FWD);
     launch_forward<1>(ctx, 1, nullptr, ctx->d_post);
     phase_end(ctx, ITR_PH_POST_FWD);
-    phase_begin(ctx, ITR_PH_POST_BWD);
-    launch_backward(ctx);
-    phase_end(ctx, ITR_PH_POST_BWD);
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    phase_begin(ctx, ITR_PH_POST_COMBINE);
+    CK(launch_combine(ctx));
+    phase_end(ctx, ITR_PH_POST_COMBINE);
+    phase_end(ctx, ITR_PH_POST_TOTAL);
     CK(cudaGetLastError());
     ctx->have_post = true;
     if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

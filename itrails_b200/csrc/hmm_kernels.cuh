@@ -22,6 +22,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace itr {
 
 constexpr int NSYM = 625;
@@ -111,6 +113,11 @@ __device__ __forceinline__ void matvec(const double *xs, const Cols<KT, NS, REGS
     for (int s = 0; s < NS; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.0;
     const double2 *x2 = reinterpret_cast<const double2 *>(xs);
     if (REGS) {
+#ifndef ITR_MV_VARIANT
+#define ITR_MV_VARIANT 3
+#endif
+#if ITR_MV_VARIANT == 0
+        // compiler-scheduled
 #pragma unroll
         for (int i = 0; i < KT; i += 4) {
             const double2 p = x2[i / 2], q = x2[i / 2 + 1];
@@ -122,6 +129,35 @@ __device__ __forceinline__ void matvec(const double *xs, const Cols<KT, NS, REGS
                 acc[s][3] = fma(q.y, cols.get(s, i + 3), acc[s][3]);
             }
         }
+#else
+        // The broadcast loads are fenced into ITR_MV_VARIANT groups with warp barriers
+        // (ptxas does not move shared-memory loads across them) so that each group is
+        // issued back to back and its ~30-cycle latency is paid once, overlapped with
+        // the FMAs of the previous group, instead of once per three loads.
+        constexpr int G = ITR_MV_VARIANT;
+        constexpr int PER = ((KT / 4 + G - 1) / G) * 4;      // x values per group (multiple of 4)
+        double xv[KT];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int i = g * PER; i < (g + 1) * PER && i < KT; i += 2) {
+                const double2 p = x2[i / 2];
+                xv[i] = p.x;
+                xv[i + 1] = p.y;
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < KT; i += 4) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                acc[s][0] = fma(xv[i + 0], cols.get(s, i + 0), acc[s][0]);
+                acc[s][1] = fma(xv[i + 1], cols.get(s, i + 1), acc[s][1]);
+                acc[s][2] = fma(xv[i + 2], cols.get(s, i + 2), acc[s][2]);
+                acc[s][3] = fma(xv[i + 3], cols.get(s, i + 3), acc[s][3]);
+            }
+        }
+#endif
     } else {
 #pragma unroll 2
         for (int i = 0; i < K4; i += 4) {
@@ -188,99 +224,110 @@ struct SymTile {
     }
 };
 
+// Symbol of tile position `pos` (0..63 over the current and the next tile).
+__device__ __forceinline__ unsigned tile_symbol(unsigned vcur, unsigned vnxt, int pos) {
+    const unsigned src = (pos < 32) ? vcur : vnxt;
+    return __shfl_sync(FULL, src, pos & 31);
+}
+
+#ifndef ITR_UNROLL_FWD
+#define ITR_UNROLL_FWD 8
+#endif
+#ifndef ITR_UNROLL_VIT
+#define ITR_UNROLL_VIT 4
+#endif
+constexpr int UNROLL_FWD = ITR_UNROLL_FWD;   // columns unrolled per loop trip (code must stay in the i-cache)
+constexpr int UNROLL_VIT = ITR_UNROLL_VIT;
+
 // ---------------------------------------------------------------------------------
 // Forward recursion.  MODE 0: log-likelihood only.  MODE 1: also store the scaled
 // alpha_t (any per-column power-of-two scale is fine: the posterior is normalised
 // per column).
 //   x_0 = pi * e(V_0);  x_t = (x_{t-1} @ a) * e(V_t)           optimizer.py:182-187
 //   loglik = log(sum x_{T-1}) + ln2 * (sum of removed exponents)  optimizer.py:160-162
+// Per column the dependent chain is: STS x -> broadcast LDS.128 -> 4 FMA chains ->
+// 2 adds -> multiply by the emission.  Everything else (symbol broadcast, emission
+// gather two columns ahead, alpha store) is issued right after the exchange so its
+// latency hides under the matvec.
 // ---------------------------------------------------------------------------------
 template <int KT, int NS, bool REGS, int MODE>
 __global__ void __launch_bounds__(256)
 forward_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ PI,
-               const double *__restrict__ Et, int K, int KP, double *__restrict__ loglik,
+               const double *__restrict__ Et, int K, double *__restrict__ loglik,
                double *__restrict__ alpha_out) {
+    constexpr int KP = 32 * NS;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *xs = smem + (size_t)warp * 2 * KP;           // double buffer
     const int n_chains = cs.n_sets * cs.n_blocks;
+    const int K4 = (K + 3) & ~3;
 
     for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
         const int set = c / cs.n_blocks;
         const int blk = cs.order[c % cs.n_blocks];
         const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
         const SymTile st{cs.sym + beg, T};
-        const double *et = Et + (size_t)set * NSYM * KP;
-        const int K4 = (K + 3) & ~3;
+        const double *etl = Et + (size_t)set * NSYM * KP + lane;
         Cols<KT, NS, REGS> acol;
         acol.load(A + (size_t)set * KP * KP, KP, lane);
 
         unsigned vcur = st.load(0, lane);
         unsigned vnxt = st.load(32, lane);
-        double x[NS];
+        double x[NS], e1[NS], e2[NS];
         {
             const unsigned v0 = __shfl_sync(FULL, vcur, 0);
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                x[s] = __ldg(PI + (size_t)set * KP + j) * __ldg(et + (size_t)v0 * KP + j);
-            }
-        }
-        long long shift = 0;
-        if (MODE == 1) {
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                if (j < K) alpha_out[(size_t)beg * K + j] = x[s];
-            }
-        }
-        // emission rows for columns t+1 and t+2 (software prefetch)
-        double e1[NS], e2[NS];
-        {
             const unsigned v1 = __shfl_sync(FULL, vcur, 1), v2 = __shfl_sync(FULL, vcur, 2);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                e1[s] = __ldg(et + (size_t)v1 * KP + lane + 32 * s);
-                e2[s] = __ldg(et + (size_t)v2 * KP + lane + 32 * s);
+                x[s] = __ldg(PI + (size_t)set * KP + lane + 32 * s) * __ldg(etl + v0 * KP + 32 * s);
+                e1[s] = __ldg(etl + v1 * KP + 32 * s);
+                e2[s] = __ldg(etl + v2 * KP + 32 * s);
             }
         }
+        long long shift = 0;
+        double *ao = (MODE == 1) ? alpha_out + (size_t)beg * K + lane : nullptr;
+        if (MODE == 1) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (lane + 32 * s < K) ao[32 * s] = x[s];
+        }
         int buf = 0;
-        for (int64_t t0 = 0; t0 < T; t0 += 32) {
+        auto column = [&](int s32, int64_t t0) {
+            const int64_t t = t0 + s32 + 1;            // column being produced
+            double *xb = xs + buf * KP;
 #pragma unroll
-            for (int s32 = 0; s32 < 32; ++s32) {
-                const int64_t t = t0 + s32 + 1;        // column being produced
-                if (t >= T) break;
-                // exchange x
-                double *xb = xs + buf * KP;
+            for (int s = 0; s < NS; ++s) xb[lane + 32 * s] = x[s];
+            __syncwarp();
+            buf ^= 1;
+            // emission row of column t+2 (independent of the chain)
+            const unsigned v = tile_symbol(vcur, vnxt, s32 + 3);
+            double e3[NS];
 #pragma unroll
-                for (int s = 0; s < NS; ++s) xb[lane + 32 * s] = x[s];
-                __syncwarp();
-                double y[NS];
-                matvec<KT, NS, REGS>(xb, acol, K4, y);
-                buf ^= 1;
+            for (int s = 0; s < NS; ++s) e3[s] = __ldg(etl + v * KP + 32 * s);
+            double y[NS];
+            matvec<KT, NS, REGS>(xb, acol, K4, y);
 #pragma unroll
-                for (int s = 0; s < NS; ++s) x[s] = y[s] * e1[s];
-                // rotate prefetch: column t+2
-                const int pos = s32 + 3;               // (t+2) - t0
-                const unsigned v = (pos < 32) ? __shfl_sync(FULL, vcur, pos & 31)
-                                              : __shfl_sync(FULL, vnxt, pos & 31);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    e1[s] = e2[s];
-                    e2[s] = __ldg(et + (size_t)v * KP + lane + 32 * s);
-                }
-                if ((s32 & (RESCALE - 1)) == RESCALE - 1) shift += rescale_pow2<NS>(x);
-                if (MODE == 1) {
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const int j = lane + 32 * s;
-                        if (j < K) alpha_out[(size_t)(beg + t) * K + j] = x[s];
-                    }
-                }
+            for (int s = 0; s < NS; ++s) {
+                x[s] = y[s] * e1[s];
+                e1[s] = e2[s];
+                e2[s] = e3[s];
             }
+            if ((s32 & (RESCALE - 1)) == RESCALE - 1) shift += rescale_pow2<NS>(x);
+            if (MODE == 1) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (lane + 32 * s < K) ao[(size_t)t * K + 32 * s] = x[s];
+            }
+        };
+        int64_t t0 = 0;
+        for (; t0 + 32 < T; t0 += 32) {                 // whole tile in range
+#pragma unroll UNROLL_FWD
+            for (int s32 = 0; s32 < 32; ++s32) column(s32, t0);
             vcur = vnxt;
             vnxt = st.load(t0 + 64, lane);
         }
+#pragma unroll 1
+        for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32, t0);
         double tot = 0.0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) tot += x[s];
@@ -292,248 +339,318 @@ forward_kernel(ChainSet cs, const double *__restrict__ A, const double *__restri
 }
 
 // ---------------------------------------------------------------------------------
-// Backward recursion fused with the posterior (reference orientation):
-//   beta_{T-1} = 1;  beta_t = (beta_{t+1} * e(V_{t+1})) @ a        optimizer.py:205-212
-//   post_t = alpha_t * beta_t / sum_j(alpha_t * beta_t)            optimizer.py:231-237
-// `post` holds alpha on entry (written by forward_kernel<MODE 1>) and the posterior
-// on exit, both (sum T, K) row-major.
+// Backward recursion (reference orientation, optimizer.py:205-212):
+//   beta_{T-1} = 1;  beta_t = (beta_{t+1} * e(V_{t+1})) @ a
+// Stores the scaled beta_t as (sum T, K) row-major.  It runs concurrently with the
+// alpha-storing forward kernel on a second stream; posterior_combine_kernel then
+// forms the posterior.
 // ---------------------------------------------------------------------------------
 template <int KT, int NS, bool REGS>
 __global__ void __launch_bounds__(256)
-backward_posterior_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ Et,
-                          int K, int KP, double *__restrict__ post) {
+backward_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ Et, int K,
+                double *__restrict__ beta_out) {
+    constexpr int KP = 32 * NS;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *xs = smem + (size_t)warp * 2 * KP;
     const int n_chains = cs.n_blocks;      // set 0 only
+    const int K4 = (K + 3) & ~3;
+    const double *etl = Et + lane;
 
     for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
         const int blk = cs.order[c];
         const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
         const SymTile st{cs.sym + beg, T};
-        double *pp = post + (size_t)beg * K;
-
-        const int K4 = (K + 3) & ~3;
+        double *bo = beta_out + (size_t)beg * K + lane;
         Cols<KT, NS, REGS> acol;
         acol.load(A, KP, lane);
-        double beta[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) beta[s] = (lane + 32 * s < K) ? 1.0 : 0.0;
 
-        // walk tiles from the end: tile covers columns [t0, t0+32)
-        const int64_t t_last = T - 1;
-        int64_t t0 = t_last & ~(int64_t)31;
-        unsigned vcur = st.load(t0, lane);
-        unsigned vprv = st.load(t0 - 32, lane);
-        // t = T-1: posterior = normalised alpha
+        double beta[NS], e1[NS], e2[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            beta[s] = (lane + 32 * s < K) ? 1.0 : 0.0;
+            if (lane + 32 * s < K) bo[(size_t)(T - 1) * K + 32 * s] = beta[s];
+        }
+        // Walk backwards: step u = 0,1,... produces column t = T-2-u and needs the
+        // emission row of column t+1 = T-1-u.  Tiles are indexed from the end of the
+        // block: tile position p of tile u0 <-> column T-1-(u0+p).
+        auto load_tile = [&](int64_t u0) -> unsigned {
+            const int64_t t = T - 1 - (u0 + lane);
+            return (t >= 0 && t < T) ? (unsigned)__ldg(st.base + t) : 0u;
+        };
+        unsigned vcur = load_tile(0), vnxt = load_tile(32);
         {
-            double w[NS], tot = 0.0;
+            const unsigned v1 = __shfl_sync(FULL, vcur, 0), v2 = __shfl_sync(FULL, vcur, 1);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                w[s] = (j < K) ? pp[(size_t)t_last * K + j] * beta[s] : 0.0;
-                tot += w[s];
-            }
-            tot = warp_sum(tot);
-            const double r = 1.0 / tot;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                if (j < K) pp[(size_t)t_last * K + j] = w[s] * r;
+                e1[s] = __ldg(etl + v1 * KP + 32 * s);     // column T-1
+                e2[s] = __ldg(etl + v2 * KP + 32 * s);     // column T-2
             }
         }
-        // prefetch: emission row of column t+1 (needed to produce beta_t) and alpha_t
-        double e1[NS], a1[NS], a2[NS];
-        {
-            const unsigned v = __shfl_sync(FULL, vcur, (int)(t_last & 31));
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                e1[s] = __ldg(Et + (size_t)v * KP + j);
-                a1[s] = (j < K && t_last >= 1) ? pp[(size_t)(t_last - 1) * K + j] : 0.0;
-                a2[s] = (j < K && t_last >= 2) ? pp[(size_t)(t_last - 2) * K + j] : 0.0;
-            }
-        }
-        int buf = 0, cnt = 0;
-        for (int64_t t = t_last - 1; t >= 0; --t) {
-            // z = beta_{t+1} * e(V_{t+1})
+        int buf = 0;
+        auto column = [&](int s32, int64_t u0) {
+            const int64_t t = T - 2 - (u0 + s32);          // column being produced
             double *xb = xs + buf * KP;
 #pragma unroll
             for (int s = 0; s < NS; ++s) xb[lane + 32 * s] = beta[s] * e1[s];
             __syncwarp();
-            matvec<KT, NS, REGS>(xb, acol, K4, beta);
             buf ^= 1;
-            if (((++cnt) & (RESCALE - 1)) == 0) (void)rescale_pow2<NS>(beta);
-            // next emission row: column t (to produce beta_{t-1})
-            if ((t & 31) == 31) {           // crossed into the previous tile
-                t0 -= 32;
-                vcur = vprv;
-                vprv = st.load(t0 - 32, lane);
-            }
-            const unsigned v = __shfl_sync(FULL, vcur, (int)(t & 31));
-            double w[NS], tot = 0.0;
+            // emission row for the step after next: column T-1-(u0+s32+2)
+            const unsigned v = tile_symbol(vcur, vnxt, s32 + 2);
+            double e3[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) e3[s] = __ldg(etl + v * KP + 32 * s);
+            matvec<KT, NS, REGS>(xb, acol, K4, beta);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                e1[s] = __ldg(Et + (size_t)v * KP + j);
-                w[s] = a1[s] * beta[s];
-                tot += w[s];
-                a1[s] = a2[s];
-                a2[s] = (j < K && t >= 2) ? pp[(size_t)(t - 2) * K + j] : 0.0;
+                e1[s] = e2[s];
+                e2[s] = e3[s];
             }
-            tot = warp_sum(tot);
-            const double r = 1.0 / tot;
+            if ((s32 & (RESCALE - 1)) == RESCALE - 1) (void)rescale_pow2<NS>(beta);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                if (j < K) pp[(size_t)t * K + j] = w[s] * r;
-            }
+            for (int s = 0; s < NS; ++s)
+                if (lane + 32 * s < K) bo[(size_t)t * K + 32 * s] = beta[s];
+        };
+        int64_t u0 = 0;
+        for (; u0 + 32 < T; u0 += 32) {                     // all 32 columns have t >= 0
+#pragma unroll UNROLL_FWD
+            for (int s32 = 0; s32 < 32; ++s32) column(s32, u0);
+            vcur = vnxt;
+            vnxt = load_tile(u0 + 64);
         }
+#pragma unroll 1
+        for (int s32 = 0; T - 2 - (u0 + s32) >= 0; ++s32) column(s32, u0);
         __syncwarp();
     }
+}
+
+// post[t][j] = alpha[t][j] * beta[t][j] / sum_j(alpha[t][j] * beta[t][j])
+// (optimizer.py:231-237; scales cancel).  `post` holds alpha on entry.  HBM-bound:
+// a CTA stages COLS columns through shared memory with coalesced loads and stores.
+template <int COLS>
+__global__ void __launch_bounds__(COLS)
+posterior_combine_kernel(double *__restrict__ post, const double *__restrict__ beta, int K, int64_t n_cols) {
+    extern __shared__ __align__(16) double sm[];            // COLS * K products
+    const int64_t c0 = (int64_t)blockIdx.x * COLS;
+    const int nc = (int)min((int64_t)COLS, n_cols - c0);
+    if (nc <= 0) return;
+    const int n = nc * K;
+    double *p = post + (size_t)c0 * K;
+    const double *b = beta + (size_t)c0 * K;
+    for (int i = threadIdx.x; i < n; i += COLS) sm[i] = p[i] * b[i];
+    __syncthreads();
+    __shared__ double rcp[COLS];
+    if ((int)threadIdx.x < nc) {
+        const double *r = sm + (size_t)threadIdx.x * K;
+        double acc = 0.0;
+        for (int j = 0; j < K; ++j) acc += r[j];
+        rcp[threadIdx.x] = 1.0 / acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += COLS) p[i] = sm[i] * rcp[i / K];
 }
 
 // ---------------------------------------------------------------------------------
 // Viterbi forward sweep (max-plus), bit-exact recipe:
 //   m_ij = (omega_i + LA_ij) + LE_j ; prev_j = first argmax_i ; omega_j = max_i
 //                                                               optimizer.py:325-332
+// The add of LE_j is hoisted out of the scan without changing any decision:
+// f(s) = fl(s + LE_j) is monotone, so max_i m_ij = f(max_i s_ij) with
+// s_ij = fl(omega_i + LA_ij), and the first maximiser of m is the first maximiser of
+// s unless rounding merges s* with a smaller neighbour, i.e. unless
+// f(pred(s*)) == f(s*).  That (rare, ~2 % of columns) case is detected per lane and
+// the whole warp redoes the column with the literal two-add scan (out of line).
+// The scan keeps four independent running maxima (i mod 4) and merges them with
+// "larger value, then smaller index", which equals the sequential first-maximum.
+// Everything is branch-free selects: a divergent branch here costs more than the scan.
 // Outputs: backpointers bp[(beg+t)*KP + j] for t >= 1 (uint8), per-chunk composite
 // maps comp[chunk][j] (state at the last column of chunk c -> state at the last
 // column of chunk c-1) and the final state (first argmax of omega_{T-1},
 // optimizer.py:347).
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ void vmerge(double &va, int &ia, double vb, int ib) {
+    const bool take = (vb > va) | ((vb == va) & (ib < ia));
+    va = take ? vb : va;
+    ia = take ? ib : ia;
+}
+
+// Literal scan for one output state (column `lac` of the padded log-a matrix, read
+// from global memory): m_i = (omega_i + LA_ij) + LE_j, first maximum.
+__device__ __noinline__ void viterbi_exact_scan(const double *xb, const double *lac, int KP, int K4,
+                                                double le, double *best_out, int *arg_out) {
+    double best = __dadd_rn(__dadd_rn(xb[0], __ldg(lac)), le);
+    int arg = 0;
+    for (int i = 1; i < K4; ++i) {
+        const double m = __dadd_rn(__dadd_rn(xb[i], __ldg(lac + (size_t)i * KP)), le);
+        const bool g = m > best;
+        best = g ? m : best;
+        arg = g ? i : arg;
+    }
+    *best_out = best;
+    *arg_out = arg;
+}
+
 template <int KT, int NS, bool REGS>
 __global__ void __launch_bounds__(256)
 viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
-                       const double *__restrict__ OM0, int K, int KP,
+                       const double *__restrict__ OM0, int K,
                        uint8_t *__restrict__ bp, uint8_t *__restrict__ comp,
                        const int64_t *__restrict__ chunk_off, int32_t *__restrict__ final_state) {
+    constexpr int KP = 32 * NS;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *xs = smem + (size_t)warp * 2 * KP;
     const int n_chains = cs.n_blocks;
+    const int K4 = (K + 3) & ~3;
+    const double *etl = LEt + lane;
 
     for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
         const int blk = cs.order[c];
         const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
         const SymTile st{cs.sym + beg, T};
-        uint8_t *cmp = comp + (size_t)chunk_off[blk] * KP;
+        uint8_t *cmp = comp + (size_t)chunk_off[blk] * KP + lane;
+        uint8_t *bpl = bp + (size_t)beg * KP + lane;
 
-        const int K2 = (K + 1) & ~1;
         Cols<KT, NS, REGS> lacol;
         lacol.load(LA, KP, lane);
-        double om[NS];
+        double om[NS], e1[NS], e2[NS];
         int anc[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int j = lane + 32 * s;
-            om[s] = __ldg(OM0 + (size_t)blk * KP + j);
-            anc[s] = j;
-        }
         unsigned vcur = st.load(0, lane);
         unsigned vnxt = st.load(32, lane);
-        double e1[NS], e2[NS];
         {
             const unsigned v1 = __shfl_sync(FULL, vcur, 1), v2 = __shfl_sync(FULL, vcur, 2);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                e1[s] = __ldg(LEt + (size_t)v1 * KP + lane + 32 * s);
-                e2[s] = __ldg(LEt + (size_t)v2 * KP + lane + 32 * s);
+                om[s] = __ldg(OM0 + (size_t)blk * KP + lane + 32 * s);
+                anc[s] = lane + 32 * s;
+                e1[s] = __ldg(etl + v1 * KP + 32 * s);
+                e2[s] = __ldg(etl + v2 * KP + 32 * s);
             }
         }
         int buf = 0;
-        for (int64_t t0 = 0; t0 < T; t0 += 32) {
+        auto column = [&](int s32, int64_t t0) {
+            const int64_t t = t0 + s32 + 1;
+            double *xb = xs + buf * KP;
 #pragma unroll
-            for (int s32 = 0; s32 < 32; ++s32) {
-                const int64_t t = t0 + s32 + 1;
-                if (t >= T) break;
-                double *xb = xs + buf * KP;
+            for (int s = 0; s < NS; ++s) xb[lane + 32 * s] = om[s];
+            __syncwarp();
+            buf ^= 1;
+            const unsigned v = tile_symbol(vcur, vnxt, s32 + 3);
+            double e3[NS];
 #pragma unroll
-                for (int s = 0; s < NS; ++s) xb[lane + 32 * s] = om[s];
-                __syncwarp();
-                buf ^= 1;
-                const double2 *x2 = reinterpret_cast<const double2 *>(xb);
-                int arg[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) { om[s] = -CUDART_INF; arg[s] = 0; }
-                auto step2 = [&](int i) {
-                    const double2 p = x2[i / 2];
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const double m0 = __dadd_rn(__dadd_rn(p.x, lacol.get(s, i)), e1[s]);
-                        const double m1 = __dadd_rn(__dadd_rn(p.y, lacol.get(s, i + 1)), e1[s]);
-                        if (i == 0) { om[s] = m0; arg[s] = 0; }
-                        else if (m0 > om[s]) { om[s] = m0; arg[s] = i; }
-                        if (m1 > om[s]) { om[s] = m1; arg[s] = i + 1; }
-                    }
-                };
-                if (REGS) {
-#pragma unroll
-                    for (int i = 0; i < KT; i += 2) step2(i);
-                } else {
-#pragma unroll 2
-                    for (int i = 0; i < K2; i += 2) step2(i);
-                }
-                // backpointers for column t
+            for (int s = 0; s < NS; ++s) e3[s] = __ldg(etl + v * KP + 32 * s);
+
+            const double2 *x2 = reinterpret_cast<const double2 *>(xb);
+            double b0[NS], b1[NS], b2[NS], b3[NS];
+            int i0[NS], i1[NS], i2[NS], i3[NS];
+            {
+                const double2 p = x2[0], q = x2[1];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j < KP) bp[(size_t)(beg + t) * KP + j] = (uint8_t)arg[s];
-                }
-                // chunk composite: anc_t[j] = anc_{t-1}[arg_j]  (reset at chunk start)
-                const bool first = (t % VCHUNK) == 0;
-                const bool last = ((t % VCHUNK) == VCHUNK - 1) || (t == T - 1);
-                int na[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    // gather anc[arg]: arg may live in any lane / slot
-                    int g = arg[s];
-#pragma unroll
-                    for (int q = 0; q < NS; ++q) {
-                        const int got = __shfl_sync(FULL, anc[q], arg[s] & 31);
-                        if ((arg[s] >> 5) == q) g = got;
-                    }
-                    na[s] = first ? arg[s] : g;
-                }
-#pragma unroll
-                for (int s = 0; s < NS; ++s) anc[s] = na[s];
-                if (last && t >= VCHUNK) {
-                    const int64_t ch = t / VCHUNK;
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const int j = lane + 32 * s;
-                        if (j < KP) cmp[(size_t)ch * KP + j] = (uint8_t)anc[s];
-                    }
-                }
-                const int pos = s32 + 3;
-                const unsigned v = (pos < 32) ? __shfl_sync(FULL, vcur, pos & 31)
-                                              : __shfl_sync(FULL, vnxt, pos & 31);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    e1[s] = e2[s];
-                    e2[s] = __ldg(LEt + (size_t)v * KP + lane + 32 * s);
+                    b0[s] = __dadd_rn(p.x, lacol.get(s, 0)); i0[s] = 0;
+                    b1[s] = __dadd_rn(p.y, lacol.get(s, 1)); i1[s] = 1;
+                    b2[s] = __dadd_rn(q.x, lacol.get(s, 2)); i2[s] = 2;
+                    b3[s] = __dadd_rn(q.y, lacol.get(s, 3)); i3[s] = 3;
                 }
             }
+            auto scan4 = [&](int i) {
+                const double2 p = x2[i / 2], q = x2[i / 2 + 1];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const double s0 = __dadd_rn(p.x, lacol.get(s, i));
+                    const double s1 = __dadd_rn(p.y, lacol.get(s, i + 1));
+                    const double s2 = __dadd_rn(q.x, lacol.get(s, i + 2));
+                    const double s3 = __dadd_rn(q.y, lacol.get(s, i + 3));
+                    const bool g0 = s0 > b0[s], g1 = s1 > b1[s], g2 = s2 > b2[s], g3 = s3 > b3[s];
+                    b0[s] = g0 ? s0 : b0[s]; i0[s] = g0 ? i : i0[s];
+                    b1[s] = g1 ? s1 : b1[s]; i1[s] = g1 ? i + 1 : i1[s];
+                    b2[s] = g2 ? s2 : b2[s]; i2[s] = g2 ? i + 2 : i2[s];
+                    b3[s] = g3 ? s3 : b3[s]; i3[s] = g3 ? i + 3 : i3[s];
+                }
+            };
+            if (REGS) {
+#pragma unroll
+                for (int i = 4; i < KT; i += 4) scan4(i);
+            } else {
+#pragma unroll 2
+                for (int i = 4; i < K4; i += 4) scan4(i);
+            }
+            int arg[NS];
+            bool slow = false;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                vmerge(b0[s], i0[s], b1[s], i1[s]);
+                vmerge(b2[s], i2[s], b3[s], i3[s]);
+                vmerge(b0[s], i0[s], b2[s], i2[s]);
+                const double sstar = b0[s];
+                const double M = __dadd_rn(sstar, e1[s]);
+                // pred(s*): next double towards -inf (finite, non-zero s* only)
+                const long long bits = __double_as_longlong(sstar);
+                const double pred = __longlong_as_double(bits - ((bits >> 63) | 1));
+                const bool odd = (sstar == 0.0) | !(fabs(sstar) < CUDART_INF);
+                slow |= (lane + 32 * s < K) & (odd | (__dadd_rn(pred, e1[s]) == M));
+                om[s] = M;
+                arg[s] = i0[s];
+            }
+            if (__any_sync(FULL, slow)) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    viterbi_exact_scan(xb, LA + lane + 32 * s, KP, K4, e1[s], &om[s], &arg[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                e1[s] = e2[s];
+                e2[s] = e3[s];
+                bpl[(size_t)t * KP + 32 * s] = (uint8_t)arg[s];
+            }
+            // chunk composite: anc_t[j] = anc_{t-1}[arg_j]  (reset at chunk start)
+            const bool first = (t % VCHUNK) == 0;
+            const bool last = ((t % VCHUNK) == VCHUNK - 1) || (t == T - 1);
+            int na[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                int g = arg[s];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    const int got = __shfl_sync(FULL, anc[q], arg[s] & 31);
+                    g = ((arg[s] >> 5) == q) ? got : g;
+                }
+                na[s] = first ? arg[s] : g;
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) anc[s] = na[s];
+            if (last && t >= VCHUNK) {
+                const int64_t ch = t / VCHUNK;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) cmp[(size_t)ch * KP + 32 * s] = (uint8_t)anc[s];
+            }
+        };
+        int64_t t0 = 0;
+        for (; t0 + 32 < T; t0 += 32) {
+#pragma unroll UNROLL_VIT
+            for (int s32 = 0; s32 < 32; ++s32) column(s32, t0);
             vcur = vnxt;
             vnxt = st.load(t0 + 64, lane);
         }
+#pragma unroll 1
+        for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32, t0);
         // first argmax of omega_{T-1}
         double best = -CUDART_INF;
-        int bi = 0x7fffffff;
+        int bidx = 0x7fffffff;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const int j = lane + 32 * s;
-            if (j < K && (bi == 0x7fffffff || om[s] > best)) { best = om[s]; bi = j; }
+            if (j < K && (bidx == 0x7fffffff || om[s] > best)) { best = om[s]; bidx = j; }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             const double ob = __shfl_xor_sync(FULL, best, o);
-            const int oi = __shfl_xor_sync(FULL, bi, o);
-            if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) {
-                best = ob; bi = oi;
+            const int oi = __shfl_xor_sync(FULL, bidx, o);
+            if (oi != 0x7fffffff && (bidx == 0x7fffffff || ob > best || (ob == best && oi < bidx))) {
+                best = ob; bidx = oi;
             }
         }
-        if (lane == 0) final_state[blk] = bi;
+        if (lane == 0) final_state[blk] = bidx;
         __syncwarp();
     }
 }
