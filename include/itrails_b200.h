@@ -94,6 +94,13 @@ int itr_build_model(itr_ctx *ctx, int n_sets, const double *params, int n_int_AB
 /* Number of hidden states for a discretisation
  * (get_emission_prob_mat.py:789-791). */
 int itr_num_states(int n_int_AB, int n_int_ABC);
+/* Parameter-independent plan of the model build for a discretisation (host only, needs
+ * no GPU): number of hidden states, matrix exponentials per parameter set, block
+ * mat-vec operations and peak number of live path keys
+ * (run_markov_chain_ABC.py:350-518 bookkeeping), and the sorted hidden-state tuples
+ * (get_trans_emiss.py:148-153; hidden is K x 3, nullable).  Returns 0 or ITR_ERR_ARG. */
+int itr_plan_info(int n_int_AB, int n_int_ABC, int32_t *K, int32_t *n_mats, int64_t *n_ops,
+                  int64_t *n_keys, int32_t *hidden);
 
 /* ---- recursions ------------------------------------------------------------------ */
 

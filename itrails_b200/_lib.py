@@ -45,6 +45,7 @@ SIGNATURES = {
     "itr_build_model": (ctypes.c_int, [_c_ctx, ctypes.c_int, _dp, ctypes.c_int, ctypes.c_int,
                                        _dp, _dp, _dp, _dp, _dp, _i32p]),
     "itr_num_states": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "itr_plan_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _i32p, _i32p, _i64p, _i64p, _i32p]),
     "itr_loglik": (ctypes.c_int, [_c_ctx, _dp, _dp]),
     "itr_viterbi": (ctypes.c_int, [_c_ctx, _dp, _dp, _dp, _u8p]),
     "itr_viterbi_fetch": (ctypes.c_int, [_c_ctx, _u8p]),

@@ -21,6 +21,7 @@
 
 #include "hmm_kernels.cuh"
 #include "model_build.h"
+#include "model_plan.h"
 
 using namespace itr;
 
@@ -374,6 +375,28 @@ extern "C" int itr_set_model(itr_ctx *ctx, int n_sets, int K, const double *a, c
 extern "C" int itr_num_states(int n_int_AB, int n_int_ABC) {
     if (n_int_AB < 1 || n_int_ABC < 1) return -1;
     return n_int_AB * n_int_ABC + 3 * n_int_ABC + 3 * (n_int_ABC * (n_int_ABC - 1) / 2);
+}
+
+extern "C" int itr_plan_info(int n_int_AB, int n_int_ABC, int32_t *K, int32_t *n_mats, int64_t *n_ops,
+                             int64_t *n_keys, int32_t *hidden) {
+    if (n_int_AB < 1 || n_int_ABC < 1) return ITR_ERR_ARG;
+    try {
+        itr::ModelPlan plan;
+        plan.build(n_int_AB, n_int_ABC);
+        if (K) *K = plan.K;
+        if (n_mats) *n_mats = plan.n_mats;
+        if (n_ops) *n_ops = (int64_t)plan.ops.size();
+        if (n_keys) *n_keys = plan.n_keys_max;
+        if (hidden)
+            for (int k = 0; k < plan.K; ++k) {
+                hidden[3 * k] = plan.hidden[k].topo;
+                hidden[3 * k + 1] = plan.hidden[k].i;
+                hidden[3 * k + 2] = plan.hidden[k].j;
+            }
+    } catch (...) {
+        return ITR_ERR_ARG;
+    }
+    return ITR_OK;
 }
 
 extern "C" int itr_build_model(itr_ctx *ctx, int n_sets, const double *params, int n_int_AB, int n_int_ABC,

@@ -6,7 +6,7 @@
 
 #include <string>
 
-struct ModelPlan;
+struct BuilderState;
 
 class ModelBuilder {
   public:
@@ -21,5 +21,5 @@ class ModelBuilder {
               const double **d_pi, int32_t *hidden, int64_t *launched, std::string &msg);
 
   private:
-    ModelPlan *plan_ = nullptr;
+    BuilderState *state_ = nullptr;
 };
