@@ -128,6 +128,17 @@ int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path);
 int itr_posterior(itr_ctx *ctx, double *post);
 int itr_posterior_fetch(itr_ctx *ctx, double *post);
 
+/* ---- overlapping the recursions ---------------------------------------------------
+ * Every recursion runs on its own CUDA stream.  By default each call returns when its
+ * result is complete.  With itr_set_async(ctx, 1), itr_loglik / itr_viterbi /
+ * itr_posterior only enqueue their work and return; independent recursions then run
+ * concurrently on the device, and all host outputs (total, per_block, path, post) are
+ * valid after itr_sync(ctx).  Device-to-host copies overlap only into page-locked
+ * buffers; into pageable memory they complete before the call returns.  Changing the
+ * blocks or the model always waits for enqueued work first. */
+int itr_set_async(itr_ctx *ctx, int on);
+int itr_sync(itr_ctx *ctx);
+
 /* ---- introspection --------------------------------------------------------------- */
 
 enum itr_phase {

@@ -51,6 +51,8 @@ SIGNATURES = {
     "itr_viterbi_fetch": (ctypes.c_int, [_c_ctx, _u8p]),
     "itr_posterior": (ctypes.c_int, [_c_ctx, _dp]),
     "itr_posterior_fetch": (ctypes.c_int, [_c_ctx, _dp]),
+    "itr_set_async": (ctypes.c_int, [_c_ctx, ctypes.c_int]),
+    "itr_sync": (ctypes.c_int, [_c_ctx]),
     "itr_phase_ms": (ctypes.c_double, [_c_ctx, ctypes.c_int]),
     "itr_launch_count": (ctypes.c_int64, [_c_ctx]),
     "itr_total_columns": (ctypes.c_int64, [_c_ctx]),

@@ -29,8 +29,14 @@ static thread_local std::string g_create_error;
 
 struct itr_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // `stream` carries block uploads and model installs; every recursion has its own
+    // stream (forward log-likelihood, Viterbi, posterior forward + combine, posterior
+    // backward) so that independent recursions overlap on the device.
+    cudaStream_t stream = nullptr, s_ll = nullptr, s_vit = nullptr, s_post = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ready = nullptr;
+    bool async = false;
+    double *pend_total = nullptr, *pend_per_block = nullptr;   // host outputs of a deferred itr_loglik
+    bool pend_ll = false;
     cudaDeviceProp prop{};
     std::string err;
     int64_t launches = 0;
@@ -55,7 +61,8 @@ struct itr_ctx {
     // log-likelihood
     double *d_ll = nullptr;
     size_t cap_ll = 0;
-    std::vector<double> h_ll;
+    double *h_ll = nullptr;      // pinned
+    size_t cap_hll = 0;
 
     // Viterbi
     double *d_LA = nullptr, *d_LEt = nullptr, *d_OM0 = nullptr, *d_tmp = nullptr;
@@ -164,14 +171,16 @@ extern "C" int itr_create(int device, itr_ctx **out) {
         return ITR_ERR_UNSUPPORTED;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (cudaStream_t *st : {&ctx->s_ll, &ctx->s_vit, &ctx->s_post, &ctx->stream2})
+        if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
         if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
         if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
-    if ((e = cudaMalloc((void **)&ctx->d_queue, 4 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_queue, 8 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
     // symbol digit table: read_data.py:6-24 ordering
     {
         std::vector<uint16_t> dig(NSYM);
@@ -195,9 +204,10 @@ extern "C" int itr_create(int device, itr_ctx **out) {
 extern "C" void itr_destroy(itr_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    for (cudaStream_t st : {ctx->stream, ctx->s_ll, ctx->s_vit, ctx->s_post, ctx->stream2})
+        if (st) cudaStreamSynchronize(st);
     delete ctx->builder;
+    if (ctx->h_ll) cudaFreeHost(ctx->h_ll);
     void *ptrs[] = {ctx->d_sym, ctx->d_off, ctx->d_order, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_queue,
                     ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
@@ -210,7 +220,9 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    for (cudaStream_t st : {ctx->s_ll, ctx->s_vit, ctx->s_post, ctx->stream2})
+        if (st) cudaStreamDestroy(st);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -243,8 +255,13 @@ extern "C" int64_t itr_num_blocks(const itr_ctx *ctx) { return ctx ? ctx->n_bloc
 // ---------------------------------------------------------------------------------
 // blocks
 // ---------------------------------------------------------------------------------
+// Data or model are about to change: drain every recursion stream first.
+static int quiesce(itr_ctx *ctx);
+
 static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off, int64_t n_blocks) {
     CK(cudaSetDevice(ctx->device));
+    int qrc = quiesce(ctx);
+    if (qrc) return qrc;
     const int64_t n_cols = off[n_blocks];
     std::vector<int32_t> order(n_blocks);
     std::iota(order.begin(), order.end(), 0);
@@ -283,6 +300,7 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(cudaMemcpyAsync(ctx->d_chunk_off, chunk_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_chunk_blk, chunk_blk.data(), (size_t)n_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     ctx->h_off.assign(off, off + n_blocks + 1);
     ctx->n_blocks = n_blocks;
     ctx->n_cols = n_cols;
@@ -334,9 +352,18 @@ extern "C" int itr_load_blocks_i64(itr_ctx *ctx, const int64_t *sym, const int64
 // ---------------------------------------------------------------------------------
 static int padded_K(int K) { return ((K + 31) / 32) * 32; }
 
+static void finish_loglik(itr_ctx *ctx);
+static int quiesce(itr_ctx *ctx) {
+    for (cudaStream_t st : {ctx->s_ll, ctx->s_vit, ctx->s_post, ctx->stream2}) CK(cudaStreamSynchronize(st));
+    finish_loglik(ctx);
+    return ITR_OK;
+}
+
 // Installs a model whose raw arrays are already on the device.
 int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, const double *d_b, const double *d_pi) {
     const int KP = padded_K(K);
+    int qrc = quiesce(ctx);
+    if (qrc) return qrc;
     CK(ensure(ctx->d_A, ctx->cap_A, (size_t)n_sets * KP * KP));
     CK(ensure(ctx->d_PI, ctx->cap_PI, (size_t)n_sets * KP));
     CK(ensure(ctx->d_Et, ctx->cap_Et, (size_t)n_sets * NSYM * KP));
@@ -347,6 +374,7 @@ int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, con
     phase_end(ctx, ITR_PH_EMIT_TABLE);
     ctx->launches += 3;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     ctx->n_sets = n_sets;
     ctx->K = K;
     ctx->KP = KP;
@@ -485,16 +513,16 @@ static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
 #endif
 
 template <int MODE>
-static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha) {
+static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha, cudaStream_t st, int slot) {
     const int K = ctx->K, KP = ctx->KP;
     const Geometry g = geometry(ctx, (int64_t)n_sets * ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    const ChainSet cs = chain_set(ctx, n_sets, 0);
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), ctx->stream);
+    const ChainSet cs = chain_set(ctx, n_sets, slot);
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
 #define FWD_REG(KT) \
-    forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
+    forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
 #define FWD_GEN(NS) \
-    forward_kernel<4, NS, false, MODE><<<g.grid, g.warps * 32, sh, ctx->stream>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
+    forward_kernel<4, NS, false, MODE><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
     ITR_DISPATCH_K(K, FWD_REG, FWD_GEN);
 #undef FWD_REG
 #undef FWD_GEN
@@ -516,32 +544,32 @@ static void launch_backward(itr_ctx *ctx, cudaStream_t st) {
 }
 
 template <int COLS>
-static cudaError_t launch_combine_t(itr_ctx *ctx) {
+static cudaError_t launch_combine_t(itr_ctx *ctx, cudaStream_t st) {
     const size_t sh = (size_t)COLS * ctx->K * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(posterior_combine_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return e;
-    posterior_combine_kernel<COLS><<<blocks_for((size_t)ctx->n_cols, COLS), COLS, sh, ctx->stream>>>(ctx->d_post, ctx->d_beta, ctx->K, ctx->n_cols);
+    posterior_combine_kernel<COLS><<<blocks_for((size_t)ctx->n_cols, COLS), COLS, sh, st>>>(ctx->d_post, ctx->d_beta, ctx->K, ctx->n_cols);
     ctx->launches += 1;
     return cudaSuccess;
 }
-static cudaError_t launch_combine(itr_ctx *ctx) {
-    if (ctx->K <= 40) return launch_combine_t<256>(ctx);
-    if (ctx->K <= 160) return launch_combine_t<64>(ctx);
-    return launch_combine_t<32>(ctx);
+static cudaError_t launch_combine(itr_ctx *ctx, cudaStream_t st) {
+    if (ctx->K <= 40) return launch_combine_t<256>(ctx, st);
+    if (ctx->K <= 160) return launch_combine_t<64>(ctx, st);
+    return launch_combine_t<32>(ctx, st);
 }
 
-static void launch_viterbi_forward(itr_ctx *ctx) {
+static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const int K = ctx->K, KP = ctx->KP;
     const Geometry g = geometry(ctx, ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
     const ChainSet cs = chain_set(ctx, 1, 2);
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), ctx->stream);
-#define VIT_REG(KT)                                                                 \
-    viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, ctx->stream>>>( \
-        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
-#define VIT_GEN(NS)                                                                  \
-    viterbi_forward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, ctx->stream>>>( \
-        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_comp, ctx->d_chunk_off, ctx->d_final)
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+#define VIT_REG(KT)                                                        \
+    viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, st>>>( \
+        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
+#define VIT_GEN(NS)                                                         \
+    viterbi_forward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, st>>>( \
+        cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
     ITR_DISPATCH_K(K, VIT_REG, VIT_GEN);
 #undef VIT_REG
 #undef VIT_GEN
@@ -554,6 +582,44 @@ static int need_ready(itr_ctx *ctx, const char *who) {
     return ITR_OK;
 }
 
+// Sum the per-block log-likelihoods of a finished itr_loglik into the caller's
+// buffers: the reference accumulates block results in block order (optimizer.py:112-113).
+static void finish_loglik(itr_ctx *ctx) {
+    if (!ctx->pend_ll) return;
+    const size_t n = (size_t)ctx->n_sets * ctx->n_blocks;
+    if (ctx->pend_per_block) memcpy(ctx->pend_per_block, ctx->h_ll, n * sizeof(double));
+    if (ctx->pend_total) {
+        for (int s = 0; s < ctx->n_sets; ++s) {
+            double acc = 0.0;
+            const double *p = ctx->h_ll + (size_t)s * ctx->n_blocks;
+            for (int64_t b = 0; b < ctx->n_blocks; ++b) acc += p[b];
+            ctx->pend_total[s] = acc;
+        }
+    }
+    ctx->pend_ll = false;
+}
+
+// ---------------------------------------------------------------------------------
+// asynchronous mode
+// ---------------------------------------------------------------------------------
+extern "C" int itr_set_async(itr_ctx *ctx, int on) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!on) {
+        int rc = itr_sync(ctx);
+        if (rc) return rc;
+    }
+    ctx->async = on != 0;
+    return ITR_OK;
+}
+
+extern "C" int itr_sync(itr_ctx *ctx) {
+    if (!ctx) return ITR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (cudaStream_t st : {ctx->stream, ctx->s_ll, ctx->s_vit, ctx->s_post, ctx->stream2}) CK(cudaStreamSynchronize(st));
+    finish_loglik(ctx);
+    return ITR_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // forward log-likelihood
 // ---------------------------------------------------------------------------------
@@ -563,24 +629,32 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
     if (rc) return rc;
     if (!total && !per_block) return fail(ctx, ITR_ERR_ARG, "itr_loglik: total and per_block are both NULL");
     CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->s_ll;
+    if (ctx->pend_ll) {            // a previous deferred call still owns the staging buffer
+        CK(cudaStreamSynchronize(st));
+        finish_loglik(ctx);
+    }
     const size_t n = (size_t)ctx->n_sets * ctx->n_blocks;
     CK(ensure(ctx->d_ll, ctx->cap_ll, n));
-    phase_begin(ctx, ITR_PH_LOGLIK);
-    launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr);
-    phase_end(ctx, ITR_PH_LOGLIK);
+    if (n > ctx->cap_hll) {
+        if (ctx->h_ll) cudaFreeHost(ctx->h_ll);
+        ctx->h_ll = nullptr;
+        ctx->cap_hll = 0;
+        CK(cudaMallocHost((void **)&ctx->h_ll, n * sizeof(double)));
+        ctx->cap_hll = n;
+    }
+    CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    phase_begin(ctx, ITR_PH_LOGLIK, st);
+    launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr, st, 0);
+    phase_end(ctx, ITR_PH_LOGLIK, st);
     CK(cudaGetLastError());
-    ctx->h_ll.resize(n);
-    CK(cudaMemcpyAsync(ctx->h_ll.data(), ctx->d_ll, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (per_block) memcpy(per_block, ctx->h_ll.data(), n * sizeof(double));
-    if (total) {
-        // the reference accumulates block results in block order (optimizer.py:112-113)
-        for (int s = 0; s < ctx->n_sets; ++s) {
-            double acc = 0.0;
-            const double *p = ctx->h_ll.data() + (size_t)s * ctx->n_blocks;
-            for (int64_t b = 0; b < ctx->n_blocks; ++b) acc += p[b];
-            total[s] = acc;
-        }
+    CK(cudaMemcpyAsync(ctx->h_ll, ctx->d_ll, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ctx->pend_total = total;
+    ctx->pend_per_block = per_block;
+    ctx->pend_ll = true;
+    if (!ctx->async) {
+        CK(cudaStreamSynchronize(st));
+        finish_loglik(ctx);
     }
     return ITR_OK;
 }
@@ -588,6 +662,14 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
 // ---------------------------------------------------------------------------------
 // Viterbi
 // ---------------------------------------------------------------------------------
+template <typename F>
+static cudaError_t chunk_smem(F kernel, size_t per_warp, int *warps, size_t *bytes) {
+    int w = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(96 * 1024) / per_warp));
+    *warps = w;
+    *bytes = per_warp * w;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes);
+}
+
 extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_E, const double *omega0,
                            uint8_t *path) {
     if (!ctx) return ITR_ERR_ARG;
@@ -595,41 +677,52 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
     if (rc) return rc;
     if (!log_a || !log_E || !omega0) return fail(ctx, ITR_ERR_ARG, "itr_viterbi: log_a, log_E and omega0 must be non-NULL");
     CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->s_vit;
     const int K = ctx->K, KP = ctx->KP;
     const int64_t nb = ctx->n_blocks;
     const double ninf = -std::numeric_limits<double>::infinity();
+    CK(cudaStreamSynchronize(st));      // buffers below may still be in use by a deferred call
     CK(ensure(ctx->d_LA, ctx->cap_LA, (size_t)KP * KP));
     CK(ensure(ctx->d_LEt, ctx->cap_LEt, (size_t)NSYM * KP));
     CK(ensure(ctx->d_OM0, ctx->cap_OM0, (size_t)nb * KP));
-    const size_t ntmp = std::max<size_t>((size_t)K * NSYM, (size_t)nb * K) + (size_t)K * K;
-    CK(ensure(ctx->d_tmp, ctx->cap_tmp, ntmp));
+    const size_t n_la = (size_t)K * K, n_le = (size_t)K * NSYM, n_om = (size_t)nb * K;
+    CK(ensure(ctx->d_tmp, ctx->cap_tmp, n_la + n_le + n_om));
     CK(ensure(ctx->d_bp, ctx->cap_bp, (size_t)(ctx->n_cols + 1) * KP));
     CK(ensure(ctx->d_comp, ctx->cap_comp, (size_t)(ctx->n_chunks + 1) * KP));
     CK(ensure(ctx->d_chunk_end, ctx->cap_chunk_end, (size_t)ctx->n_chunks + 1));
     CK(ensure(ctx->d_path, ctx->cap_path, (size_t)ctx->n_cols));
     CK(ensure(ctx->d_final, ctx->cap_final, (size_t)nb));
-    double *t_la = ctx->d_tmp, *t_big = ctx->d_tmp + (size_t)K * K;
-    CK(cudaMemcpyAsync(t_la, log_a, (size_t)K * K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    pad_kernel<<<blocks_for((size_t)KP * KP, 256), 256, 0, ctx->stream>>>(t_la, ctx->d_LA, 1, K, K, KP, KP, ninf);
-    CK(cudaMemcpyAsync(t_big, log_E, (size_t)K * NSYM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    transpose_table_kernel<<<blocks_for((size_t)NSYM * KP, 256), 256, 0, ctx->stream>>>(t_big, ctx->d_LEt, K, KP, 0.0);
-    CK(cudaMemcpyAsync(t_big, omega0, (size_t)nb * K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    pad_kernel<<<blocks_for((size_t)nb * KP, 256), 256, 0, ctx->stream>>>(t_big, ctx->d_OM0, (int)nb, 1, K, 1, KP, ninf);
+    double *t_la = ctx->d_tmp, *t_le = t_la + n_la, *t_om = t_le + n_le;
+    CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    CK(cudaMemcpyAsync(t_la, log_a, n_la * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t_le, log_E, n_le * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t_om, omega0, n_om * sizeof(double), cudaMemcpyHostToDevice, st));
+    pad_kernel<<<blocks_for((size_t)KP * KP, 256), 256, 0, st>>>(t_la, ctx->d_LA, 1, K, K, KP, KP, ninf);
+    transpose_table_kernel<<<blocks_for((size_t)NSYM * KP, 256), 256, 0, st>>>(t_le, ctx->d_LEt, K, KP, 0.0);
+    pad_kernel<<<blocks_for((size_t)nb * KP, 256), 256, 0, st>>>(t_om, ctx->d_OM0, (int)nb, 1, K, 1, KP, ninf);
     ctx->launches += 3;
-    phase_begin(ctx, ITR_PH_VITERBI_FWD);
-    launch_viterbi_forward(ctx);
-    phase_end(ctx, ITR_PH_VITERBI_FWD);
-    phase_begin(ctx, ITR_PH_VITERBI_TRACE);
-    viterbi_boundary_kernel<<<blocks_for((size_t)nb, 128), 128, 0, ctx->stream>>>(ctx->d_off, ctx->d_chunk_off, ctx->d_comp,
-                                                                                ctx->d_final, KP, (int)nb, ctx->d_chunk_end);
-    viterbi_traceback_kernel<<<blocks_for((size_t)ctx->n_chunks, 128), 128, 0, ctx->stream>>>(
-        ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, ctx->d_chunk_end, KP, ctx->n_chunks, ctx->d_path);
-    phase_end(ctx, ITR_PH_VITERBI_TRACE);
-    ctx->launches += 2;
+    phase_begin(ctx, ITR_PH_VITERBI_FWD, st);
+    launch_viterbi_forward(ctx, st);
+    phase_end(ctx, ITR_PH_VITERBI_FWD, st);
+    phase_begin(ctx, ITR_PH_VITERBI_TRACE, st);
+    {
+        int w1 = 1, w2 = 1;
+        size_t sh1 = 0, sh2 = 0;
+        CK(chunk_smem(viterbi_compose_kernel, (size_t)VCHUNK * KP, &w1, &sh1));
+        CK(chunk_smem(viterbi_traceback_kernel, (size_t)VCHUNK * KP + VCHUNK, &w2, &sh2));
+        viterbi_compose_kernel<<<blocks_for((size_t)ctx->n_chunks, w1), w1 * 32, sh1, st>>>(
+            ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, KP, K, ctx->n_chunks, ctx->d_comp);
+        viterbi_boundary_kernel<<<blocks_for((size_t)nb, 128), 128, 0, st>>>(ctx->d_off, ctx->d_chunk_off, ctx->d_comp,
+                                                                            ctx->d_final, KP, (int)nb, ctx->d_chunk_end);
+        viterbi_traceback_kernel<<<blocks_for((size_t)ctx->n_chunks, w2), w2 * 32, sh2, st>>>(
+            ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, ctx->d_chunk_end, KP, ctx->n_chunks, ctx->d_path);
+    }
+    phase_end(ctx, ITR_PH_VITERBI_TRACE, st);
+    ctx->launches += 3;
     CK(cudaGetLastError());
     ctx->have_path = true;
-    if (path) CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (path) CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, st));
+    if (!ctx->async) CK(cudaStreamSynchronize(st));
     return ITR_OK;
 }
 
@@ -638,8 +731,8 @@ extern "C" int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path) {
     if (!path) return fail(ctx, ITR_ERR_ARG, "itr_viterbi_fetch: path is NULL");
     if (!ctx->have_path) return fail(ctx, ITR_ERR_STATE, "itr_viterbi_fetch: no Viterbi result on the device");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, ctx->s_vit));
+    CK(cudaStreamSynchronize(ctx->s_vit));
     return ITR_OK;
 }
 
@@ -651,30 +744,33 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
     int rc = need_ready(ctx, "itr_posterior");
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->s_post;
     const size_t n = (size_t)ctx->n_cols * ctx->K;
+    CK(cudaStreamSynchronize(st));
     CK(ensure(ctx->d_post, ctx->cap_post, n));
     CK(ensure(ctx->d_beta, ctx->cap_beta, n));
-    // forward (alpha -> d_post) on the main stream, backward (beta -> d_beta) on the
-    // second stream, concurrently; then the combine on the main stream.
-    phase_begin(ctx, ITR_PH_POST_TOTAL);
-    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    // forward (alpha -> d_post) on the posterior stream, backward (beta -> d_beta) on
+    // the second stream, concurrently; then the combine on the posterior stream.
+    CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    phase_begin(ctx, ITR_PH_POST_TOTAL, st);
+    CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     phase_begin(ctx, ITR_PH_POST_BWD, ctx->stream2);
     launch_backward(ctx, ctx->stream2);
     phase_end(ctx, ITR_PH_POST_BWD, ctx->stream2);
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
-    phase_begin(ctx, ITR_PH_POST_FWD);
-    launch_forward<1>(ctx, 1, nullptr, ctx->d_post);
-    phase_end(ctx, ITR_PH_POST_FWD);
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    phase_begin(ctx, ITR_PH_POST_COMBINE);
-    CK(launch_combine(ctx));
-    phase_end(ctx, ITR_PH_POST_COMBINE);
-    phase_end(ctx, ITR_PH_POST_TOTAL);
+    phase_begin(ctx, ITR_PH_POST_FWD, st);
+    launch_forward<1>(ctx, 1, nullptr, ctx->d_post, st, 3);
+    phase_end(ctx, ITR_PH_POST_FWD, st);
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    phase_begin(ctx, ITR_PH_POST_COMBINE, st);
+    CK(launch_combine(ctx, st));
+    phase_end(ctx, ITR_PH_POST_COMBINE, st);
+    phase_end(ctx, ITR_PH_POST_TOTAL, st);
     CK(cudaGetLastError());
     ctx->have_post = true;
-    if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!ctx->async) CK(cudaStreamSynchronize(st));
     return ITR_OK;
 }
 
@@ -683,7 +779,7 @@ extern "C" int itr_posterior_fetch(itr_ctx *ctx, double *post) {
     if (!post) return fail(ctx, ITR_ERR_ARG, "itr_posterior_fetch: post is NULL");
     if (!ctx->have_post) return fail(ctx, ITR_ERR_STATE, "itr_posterior_fetch: no posterior on the device");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(post, ctx->d_post, (size_t)ctx->n_cols * ctx->K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(post, ctx->d_post, (size_t)ctx->n_cols * ctx->K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_post));
+    CK(cudaStreamSynchronize(ctx->s_post));
     return ITR_OK;
 }

@@ -460,42 +460,65 @@ posterior_combine_kernel(double *__restrict__ post, const double *__restrict__ b
 // s unless rounding merges s* with a smaller neighbour, i.e. unless
 // f(pred(s*)) == f(s*).  That (rare, ~2 % of columns) case is detected per lane and
 // the whole warp redoes the column with the literal two-add scan (out of line).
-// The scan keeps four independent running maxima (i mod 4) and merges them with
-// "larger value, then smaller index", which equals the sequential first-maximum.
-// Everything is branch-free selects: a divergent branch here costs more than the scan.
-// Outputs: backpointers bp[(beg+t)*KP + j] for t >= 1 (uint8), per-chunk composite
-// maps comp[chunk][j] (state at the last column of chunk c -> state at the last
-// column of chunk c-1) and the final state (first argmax of omega_{T-1},
-// optimizer.py:347).
+// The first maximiser of s is found with a tournament over (value, index) pairs: all
+// K sums are formed first (independent adds), then log2(K) levels of "right wins only
+// if strictly greater" — the left operand always holds the smaller indices, so this is
+// np.argmax's first-maximum rule — which keeps the dependent chain at 5 compare/select
+// links instead of K.  Everything is branch-free selects.
+// Outputs: backpointers bp[(beg+t)*KP + j] for t >= 1 (uint8) and the final state
+// (first argmax of omega_{T-1}, optimizer.py:347).  The traceback is parallel
+// (viterbi_compose_kernel / viterbi_boundary_kernel / viterbi_traceback_kernel).
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void vmerge(double &va, int &ia, double vb, int ib) {
-    const bool take = (vb > va) | ((vb == va) & (ib < ia));
-    va = take ? vb : va;
-    ia = take ? ib : ia;
-}
 
 // Literal scan for one output state (column `lac` of the padded log-a matrix, read
 // from global memory): m_i = (omega_i + LA_ij) + LE_j, first maximum.
-__device__ __noinline__ void viterbi_exact_scan(const double *xb, const double *lac, int KP, int K4,
-                                                double le, double *best_out, int *arg_out) {
+struct ScanResult {
+    double best;
+    int arg;
+};
+__device__ __forceinline__ ScanResult viterbi_exact_scan(const double *xb, const double *lac, int KP, int K4, double le) {
     double best = __dadd_rn(__dadd_rn(xb[0], __ldg(lac)), le);
     int arg = 0;
+#pragma unroll 1
     for (int i = 1; i < K4; ++i) {
         const double m = __dadd_rn(__dadd_rn(xb[i], __ldg(lac + (size_t)i * KP)), le);
         const bool g = m > best;
         best = g ? m : best;
         arg = g ? i : arg;
     }
-    *best_out = best;
-    *arg_out = arg;
+    return ScanResult{best, arg};
+}
+
+// In-place tournament over v[0..N): afterwards v[0] is the maximum and ix[0] the index
+// of its first occurrence.  Compile-time recursion so that every index is static.
+template <int N, int CUR>
+struct Tournament {
+    __device__ __forceinline__ static void run(double (&v)[N], int (&ix)[N]) {
+        if constexpr (CUR > 1) {
+#pragma unroll
+            for (int m = 0; m < CUR / 2; ++m) {
+                const bool g = v[2 * m + 1] > v[2 * m];
+                v[m] = g ? v[2 * m + 1] : v[2 * m];
+                ix[m] = g ? ix[2 * m + 1] : ix[2 * m];
+            }
+            if constexpr (CUR & 1) {
+                v[CUR / 2] = v[CUR - 1];
+                ix[CUR / 2] = ix[CUR - 1];
+            }
+            Tournament<N, (CUR + 1) / 2>::run(v, ix);
+        }
+    }
+};
+template <int N>
+__device__ __forceinline__ void tournament(double (&v)[N], int (&ix)[N]) {
+    Tournament<N, N>::run(v, ix);
 }
 
 template <int KT, int NS, bool REGS>
 __global__ void __launch_bounds__(256)
 viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                        const double *__restrict__ OM0, int K,
-                       uint8_t *__restrict__ bp, uint8_t *__restrict__ comp,
-                       const int64_t *__restrict__ chunk_off, int32_t *__restrict__ final_state) {
+                       uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
     constexpr int KP = 32 * NS;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -508,13 +531,11 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
         const int blk = cs.order[c];
         const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
         const SymTile st{cs.sym + beg, T};
-        uint8_t *cmp = comp + (size_t)chunk_off[blk] * KP + lane;
         uint8_t *bpl = bp + (size_t)beg * KP + lane;
 
         Cols<KT, NS, REGS> lacol;
         lacol.load(LA, KP, lane);
         double om[NS], e1[NS], e2[NS];
-        int anc[NS];
         unsigned vcur = st.load(0, lane);
         unsigned vnxt = st.load(32, lane);
         {
@@ -522,7 +543,6 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 om[s] = __ldg(OM0 + (size_t)blk * KP + lane + 32 * s);
-                anc[s] = lane + 32 * s;
                 e1[s] = __ldg(etl + v1 * KP + 32 * s);
                 e2[s] = __ldg(etl + v2 * KP + 32 * s);
             }
@@ -541,88 +561,91 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             for (int s = 0; s < NS; ++s) e3[s] = __ldg(etl + v * KP + 32 * s);
 
             const double2 *x2 = reinterpret_cast<const double2 *>(xb);
-            double b0[NS], b1[NS], b2[NS], b3[NS];
-            int i0[NS], i1[NS], i2[NS], i3[NS];
-            {
-                const double2 p = x2[0], q = x2[1];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    b0[s] = __dadd_rn(p.x, lacol.get(s, 0)); i0[s] = 0;
-                    b1[s] = __dadd_rn(p.y, lacol.get(s, 1)); i1[s] = 1;
-                    b2[s] = __dadd_rn(q.x, lacol.get(s, 2)); i2[s] = 2;
-                    b3[s] = __dadd_rn(q.y, lacol.get(s, 3)); i3[s] = 3;
-                }
-            }
-            auto scan4 = [&](int i) {
-                const double2 p = x2[i / 2], q = x2[i / 2 + 1];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const double s0 = __dadd_rn(p.x, lacol.get(s, i));
-                    const double s1 = __dadd_rn(p.y, lacol.get(s, i + 1));
-                    const double s2 = __dadd_rn(q.x, lacol.get(s, i + 2));
-                    const double s3 = __dadd_rn(q.y, lacol.get(s, i + 3));
-                    const bool g0 = s0 > b0[s], g1 = s1 > b1[s], g2 = s2 > b2[s], g3 = s3 > b3[s];
-                    b0[s] = g0 ? s0 : b0[s]; i0[s] = g0 ? i : i0[s];
-                    b1[s] = g1 ? s1 : b1[s]; i1[s] = g1 ? i + 1 : i1[s];
-                    b2[s] = g2 ? s2 : b2[s]; i2[s] = g2 ? i + 2 : i2[s];
-                    b3[s] = g3 ? s3 : b3[s]; i3[s] = g3 ? i + 3 : i3[s];
-                }
-            };
-            if (REGS) {
-#pragma unroll
-                for (int i = 4; i < KT; i += 4) scan4(i);
-            } else {
-#pragma unroll 2
-                for (int i = 4; i < K4; i += 4) scan4(i);
-            }
+            double sstar[NS];
             int arg[NS];
+            if (REGS) {
+                double sv[KT];
+                int ix[KT];
+#pragma unroll
+                for (int i = 0; i < KT; i += 2) {
+                    const double2 p = x2[i / 2];
+                    sv[i] = __dadd_rn(p.x, lacol.get(0, i));
+                    sv[i + 1] = __dadd_rn(p.y, lacol.get(0, i + 1));
+                    ix[i] = i;
+                    ix[i + 1] = i + 1;
+                }
+                tournament<KT>(sv, ix);
+                sstar[0] = sv[0];
+                arg[0] = ix[0];
+            } else {
+                // K > 32: four running first-maxima (i mod 4) per owned state, merged with
+                // "larger value, then smaller index"
+                double b0[NS], b1[NS], b2[NS], b3[NS];
+                int i0[NS], i1[NS], i2[NS], i3[NS];
+                {
+                    const double2 p = x2[0], q = x2[1];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        b0[s] = __dadd_rn(p.x, lacol.get(s, 0)); i0[s] = 0;
+                        b1[s] = __dadd_rn(p.y, lacol.get(s, 1)); i1[s] = 1;
+                        b2[s] = __dadd_rn(q.x, lacol.get(s, 2)); i2[s] = 2;
+                        b3[s] = __dadd_rn(q.y, lacol.get(s, 3)); i3[s] = 3;
+                    }
+                }
+#pragma unroll 2
+                for (int i = 4; i < K4; i += 4) {
+                    const double2 p = x2[i / 2], q = x2[i / 2 + 1];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const double s0 = __dadd_rn(p.x, lacol.get(s, i));
+                        const double s1 = __dadd_rn(p.y, lacol.get(s, i + 1));
+                        const double s2 = __dadd_rn(q.x, lacol.get(s, i + 2));
+                        const double s3 = __dadd_rn(q.y, lacol.get(s, i + 3));
+                        const bool g0 = s0 > b0[s], g1 = s1 > b1[s], g2 = s2 > b2[s], g3 = s3 > b3[s];
+                        b0[s] = g0 ? s0 : b0[s]; i0[s] = g0 ? i : i0[s];
+                        b1[s] = g1 ? s1 : b1[s]; i1[s] = g1 ? i + 1 : i1[s];
+                        b2[s] = g2 ? s2 : b2[s]; i2[s] = g2 ? i + 2 : i2[s];
+                        b3[s] = g3 ? s3 : b3[s]; i3[s] = g3 ? i + 3 : i3[s];
+                    }
+                }
+                auto vmerge = [](double &va, int &ia, double vb, int ib) {
+                    const bool take = (vb > va) | ((vb == va) & (ib < ia));
+                    va = take ? vb : va;
+                    ia = take ? ib : ia;
+                };
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    vmerge(b0[s], i0[s], b1[s], i1[s]);
+                    vmerge(b2[s], i2[s], b3[s], i3[s]);
+                    vmerge(b0[s], i0[s], b2[s], i2[s]);
+                    sstar[s] = b0[s];
+                    arg[s] = i0[s];
+                }
+            }
             bool slow = false;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                vmerge(b0[s], i0[s], b1[s], i1[s]);
-                vmerge(b2[s], i2[s], b3[s], i3[s]);
-                vmerge(b0[s], i0[s], b2[s], i2[s]);
-                const double sstar = b0[s];
-                const double M = __dadd_rn(sstar, e1[s]);
+                const double M = __dadd_rn(sstar[s], e1[s]);
                 // pred(s*): next double towards -inf (finite, non-zero s* only)
-                const long long bits = __double_as_longlong(sstar);
+                const long long bits = __double_as_longlong(sstar[s]);
                 const double pred = __longlong_as_double(bits - ((bits >> 63) | 1));
-                const bool odd = (sstar == 0.0) | !(fabs(sstar) < CUDART_INF);
+                const bool odd = (sstar[s] == 0.0) | !(fabs(sstar[s]) < CUDART_INF);
                 slow |= (lane + 32 * s < K) & (odd | (__dadd_rn(pred, e1[s]) == M));
                 om[s] = M;
-                arg[s] = i0[s];
             }
             if (__any_sync(FULL, slow)) {
 #pragma unroll
-                for (int s = 0; s < NS; ++s)
-                    viterbi_exact_scan(xb, LA + lane + 32 * s, KP, K4, e1[s], &om[s], &arg[s]);
+                for (int s = 0; s < NS; ++s) {
+                    const ScanResult r = viterbi_exact_scan(xb, LA + lane + 32 * s, KP, K4, e1[s]);
+                    om[s] = r.best;
+                    arg[s] = r.arg;
+                }
             }
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 e1[s] = e2[s];
                 e2[s] = e3[s];
                 bpl[(size_t)t * KP + 32 * s] = (uint8_t)arg[s];
-            }
-            // chunk composite: anc_t[j] = anc_{t-1}[arg_j]  (reset at chunk start)
-            const bool first = (t % VCHUNK) == 0;
-            const bool last = ((t % VCHUNK) == VCHUNK - 1) || (t == T - 1);
-            int na[NS];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                int g = arg[s];
-#pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    const int got = __shfl_sync(FULL, anc[q], arg[s] & 31);
-                    g = ((arg[s] >> 5) == q) ? got : g;
-                }
-                na[s] = first ? arg[s] : g;
-            }
-#pragma unroll
-            for (int s = 0; s < NS; ++s) anc[s] = na[s];
-            if (last && t >= VCHUNK) {
-                const int64_t ch = t / VCHUNK;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) cmp[(size_t)ch * KP + 32 * s] = (uint8_t)anc[s];
             }
         };
         int64_t t0 = 0;
@@ -655,7 +678,37 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
     }
 }
 
-// One thread per block: end state of every traceback chunk.
+// Parallel traceback, step 1: one warp per VCHUNK-column chunk.  The chunk's
+// backpointer rows are staged in shared memory with coalesced 16-byte loads; lane j
+// then follows them from state j at the chunk's last column to the state at the last
+// column of the previous chunk: comp[chunk][j].
+__global__ void __launch_bounds__(128)
+viterbi_compose_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ chunk_off,
+                       const int32_t *__restrict__ chunk_blk, const uint8_t *__restrict__ bp, int KP, int K,
+                       int64_t n_chunks, uint8_t *__restrict__ comp) {
+    extern __shared__ __align__(16) uint8_t sbp[];            // warps x VCHUNK x KP
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (g >= n_chunks) return;
+    const int blk = chunk_blk[g];
+    const int64_t c = g - chunk_off[blk];
+    if (c == 0) return;                                       // nothing before the first chunk
+    const int64_t beg = off[blk], T = off[blk + 1] - beg;
+    const int64_t ts = c * VCHUNK, te = min(ts + VCHUNK, T) - 1;
+    uint8_t *mine = sbp + (size_t)warp * VCHUNK * KP;
+    const int n16 = (int)((te - ts + 1) * KP / 16);
+    const uint4 *src = reinterpret_cast<const uint4 *>(bp + (size_t)(beg + ts) * KP);
+    uint4 *dst = reinterpret_cast<uint4 *>(mine);
+    for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+    __syncwarp();
+    for (int j = lane; j < K; j += 32) {
+        int s = j;
+        for (int64_t t = te; t >= ts; --t) s = mine[(size_t)(t - ts) * KP + s];
+        comp[(size_t)g * KP + j] = (uint8_t)s;
+    }
+}
+
+// Step 2, one thread per block: end state of every traceback chunk.
 __global__ void viterbi_boundary_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ chunk_off,
                                         const uint8_t *__restrict__ comp, const int32_t *__restrict__ final_state,
                                         int KP, int n_blocks, uint8_t *__restrict__ chunk_end) {
@@ -673,26 +726,40 @@ __global__ void viterbi_boundary_kernel(const int64_t *__restrict__ off, const i
     }
 }
 
-// One thread per traceback chunk: follow the backpointers inside the chunk from its
-// known end state (optimizer.py:349-352) and write the path bytes.
-__global__ void viterbi_traceback_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ chunk_off,
-                                         const int32_t *__restrict__ chunk_blk,
-                                         const uint8_t *__restrict__ bp, const uint8_t *__restrict__ chunk_end,
-                                         int KP, int64_t n_chunks, uint8_t *__restrict__ path) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Step 3, one warp per chunk: stage the chunk's backpointers in shared memory, follow
+// them from the chunk's known end state (optimizer.py:349-352) and write the path bytes
+// with coalesced stores.
+__global__ void __launch_bounds__(128)
+viterbi_traceback_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ chunk_off,
+                         const int32_t *__restrict__ chunk_blk, const uint8_t *__restrict__ bp,
+                         const uint8_t *__restrict__ chunk_end, int KP, int64_t n_chunks,
+                         uint8_t *__restrict__ path) {
+    extern __shared__ __align__(16) uint8_t sbp[];            // warps x (VCHUNK x KP + VCHUNK)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (g >= n_chunks) return;
     const int blk = chunk_blk[g];
     const int64_t c = g - chunk_off[blk];
     const int64_t beg = off[blk], T = off[blk + 1] - beg;
-    const int64_t ts = c * VCHUNK;
-    const int64_t te = min(ts + VCHUNK, T) - 1;
-    int s = chunk_end[g];
-    uint8_t *p = path + beg;
-    p[te] = (uint8_t)s;
-    for (int64_t t = te; t > ts; --t) {
-        s = bp[(size_t)(beg + t) * KP + s];
-        p[t - 1] = (uint8_t)s;
+    const int64_t ts = c * VCHUNK, te = min(ts + VCHUNK, T) - 1;
+    uint8_t *mine = sbp + (size_t)warp * (VCHUNK * KP + VCHUNK);
+    uint8_t *out = mine + VCHUNK * KP;
+    const int n16 = (int)((te - ts + 1) * KP / 16);
+    const uint4 *src = reinterpret_cast<const uint4 *>(bp + (size_t)(beg + ts) * KP);
+    uint4 *dst = reinterpret_cast<uint4 *>(mine);
+    for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+    __syncwarp();
+    if (lane == 0) {
+        int s = chunk_end[g];
+        out[te - ts] = (uint8_t)s;
+        for (int64_t t = te; t > ts; --t) {
+            s = mine[(size_t)(t - ts) * KP + s];
+            out[t - 1 - ts] = (uint8_t)s;
+        }
     }
+    __syncwarp();
+    uint8_t *p = path + beg + ts;
+    for (int i = lane; i <= te - ts; i += 32) p[i] = out[i];
 }
 
 }  // namespace itr

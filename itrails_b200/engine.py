@@ -165,6 +165,16 @@ class Engine:
         off = self._offsets
         return [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
+    # -- overlap ------------------------------------------------------------------
+    def set_async(self, on=True):
+        """With ``on``, loglik / viterbi / posterior only enqueue their work (each on its
+        own CUDA stream, so independent recursions overlap on the device); host results
+        are valid after :meth:`sync`."""
+        self._ck(self._lib.itr_set_async(self._ctx, 1 if on else 0))
+
+    def sync(self):
+        self._ck(self._lib.itr_sync(self._ctx))
+
     # -- introspection -----------------------------------------------------------
     def phase_ms(self, name):
         return float(self._lib.itr_phase_ms(self._ctx, L.PHASES[name]))
