@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -560,10 +561,23 @@ static cudaError_t launch_combine(itr_ctx *ctx, cudaStream_t st) {
 
 static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const int K = ctx->K, KP = ctx->KP;
-    const Geometry g = geometry(ctx, ctx->n_blocks, 16);
-    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
     const ChainSet cs = chain_set(ctx, 1, 2);
     cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    ctx->launches += 1;
+    // Few chains: four warps per chain (latency); many chains: one warp per chain (throughput).
+    const int sms = ctx->prop.multiProcessorCount;
+    if (K <= 32 && ctx->n_blocks <= (int64_t)4 * sms && !getenv("ITR_VITERBI_1WARP")) {
+        const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)4 * sms);
+        switch ((K + 7) / 8) {
+            case 1: viterbi_forward4_kernel<2><<<grid, 128, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final); break;
+            case 2: viterbi_forward4_kernel<4><<<grid, 128, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final); break;
+            case 3: viterbi_forward4_kernel<6><<<grid, 128, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final); break;
+            default: viterbi_forward4_kernel<8><<<grid, 128, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final); break;
+        }
+        return;
+    }
+    const Geometry g = geometry(ctx, ctx->n_blocks, 16);
+    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
 #define VIT_REG(KT)                                                        \
     viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, st>>>( \
         cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
@@ -573,7 +587,6 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     ITR_DISPATCH_K(K, VIT_REG, VIT_GEN);
 #undef VIT_REG
 #undef VIT_GEN
-    ctx->launches += 1;
 }
 
 static int need_ready(itr_ctx *ctx, const char *who) {

@@ -548,17 +548,19 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             }
         }
         int buf = 0;
+        unsigned vpre = tile_symbol(vcur, vnxt, 3);      // symbol of the column two ahead
+        uint8_t *bpt = bpl + KP;                          // row of column t = 1
         auto column = [&](int s32, int64_t t0) {
-            const int64_t t = t0 + s32 + 1;
             double *xb = xs + buf * KP;
 #pragma unroll
             for (int s = 0; s < NS; ++s) xb[lane + 32 * s] = om[s];
             __syncwarp();
             buf ^= 1;
-            const unsigned v = tile_symbol(vcur, vnxt, s32 + 3);
+            // emission row two columns ahead; its symbol was shuffled out one column ago
             double e3[NS];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) e3[s] = __ldg(etl + v * KP + 32 * s);
+            for (int s = 0; s < NS; ++s) e3[s] = __ldg(etl + vpre * KP + 32 * s);
+            vpre = tile_symbol(vcur, vnxt, s32 + 4);
 
             const double2 *x2 = reinterpret_cast<const double2 *>(xb);
             double sstar[NS];
@@ -633,7 +635,7 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
                 slow |= (lane + 32 * s < K) & (odd | (__dadd_rn(pred, e1[s]) == M));
                 om[s] = M;
             }
-            if (__any_sync(FULL, slow)) {
+            if (__builtin_expect(__any_sync(FULL, slow), 0)) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     const ScanResult r = viterbi_exact_scan(xb, LA + lane + 32 * s, KP, K4, e1[s]);
@@ -645,8 +647,9 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             for (int s = 0; s < NS; ++s) {
                 e1[s] = e2[s];
                 e2[s] = e3[s];
-                bpl[(size_t)t * KP + 32 * s] = (uint8_t)arg[s];
+                bpt[32 * s] = (uint8_t)arg[s];
             }
+            bpt += KP;
         };
         int64_t t0 = 0;
         for (; t0 + 32 < T; t0 += 32) {
@@ -675,6 +678,141 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
         }
         if (lane == 0) final_state[blk] = bidx;
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Viterbi forward sweep, four warps per chain (K <= 32).  With few chains (config 2:
+// 100 blocks on 148 SMs) the sweep is bound by the per-column latency of one warp's
+// ~200-instruction argmax.  Here a CTA of four warps (one per SM sub-partition) walks
+// one chain: warp w scans the CPW = KT8/4 predecessors i in [w CPW, (w+1) CPW) for all
+// 32 successor lanes, the four (value, index) partials meet in shared memory behind one
+// bar.sync, and every warp redundantly finishes the column (merge of the partials in
+// i-order with "right wins only if strictly greater" = first maximum, hoisted emission
+// add + exactness check exactly as in viterbi_forward_kernel).  Same results bit for
+// bit; ~2.5x shorter column latency.
+// ---------------------------------------------------------------------------------
+template <int CPW>
+__global__ void __launch_bounds__(128)
+viterbi_forward4_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
+                        const double *__restrict__ OM0, int K,
+                        uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
+    constexpr int KP = 32;
+    __shared__ __align__(16) double xo[4][KP];          // each warp's private copy of omega
+    __shared__ __align__(16) double pv[2][4][KP];       // partial maxima
+    __shared__ int pidx[2][4][KP];                      // partial arg-maxima
+    __shared__ int chain_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_chains = cs.n_blocks;
+    const int K4 = (K + 3) & ~3;
+    const double *etl = LEt + lane;
+    const int i0 = warp * CPW;
+
+    // rows i0 .. i0+CPW-1 of log a, column `lane`
+    double la[CPW];
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) la[c] = __ldg(LA + (size_t)(i0 + c) * KP + lane);
+
+    for (;;) {
+        if (threadIdx.x == 0) chain_s = (int)atomicAdd(cs.queue, 1u);
+        __syncthreads();
+        const int c = chain_s;
+        __syncthreads();
+        if (c >= n_chains) break;
+        const int blk = cs.order[c];
+        const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
+        const SymTile st{cs.sym + beg, T};
+        uint8_t *bpl = bp + (size_t)beg * KP + lane;
+
+        double om = __ldg(OM0 + (size_t)blk * KP + lane);
+        unsigned vcur = st.load(0, lane);
+        unsigned vnxt = st.load(32, lane);
+        double e1, e2;
+        {
+            const unsigned v1 = __shfl_sync(FULL, vcur, 1), v2 = __shfl_sync(FULL, vcur, 2);
+            e1 = __ldg(etl + v1 * KP);
+            e2 = __ldg(etl + v2 * KP);
+        }
+        xo[warp][lane] = om;
+        __syncwarp();
+        unsigned vpre = tile_symbol(vcur, vnxt, 3);      // symbol of the column two ahead
+        uint8_t *bpt = bpl + KP;                          // row of column t = 1
+        int buf = 0;
+        auto column = [&](int s32, int64_t t0) {
+            // ---- phase A: this warp's CPW predecessors
+            const double2 *x2 = reinterpret_cast<const double2 *>(&xo[warp][i0]);
+            double sv[CPW];
+            int ix[CPW];
+#pragma unroll
+            for (int q = 0; q < CPW; q += 2) {
+                const double2 p = x2[q / 2];
+                sv[q] = __dadd_rn(p.x, la[q]);
+                sv[q + 1] = __dadd_rn(p.y, la[q + 1]);
+                ix[q] = i0 + q;
+                ix[q + 1] = i0 + q + 1;
+            }
+            // emission row two columns ahead; its symbol was shuffled out one column ago
+            const double e3 = __ldg(etl + vpre * KP);
+            vpre = tile_symbol(vcur, vnxt, s32 + 4);
+            tournament<CPW>(sv, ix);
+            pv[buf][warp][lane] = sv[0];
+            pidx[buf][warp][lane] = ix[0];
+            __syncthreads();
+            // ---- phase B: merge the four partials (ascending i ranges)
+            double mv[4];
+            int mi[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                mv[w] = pv[buf][w][lane];
+                mi[w] = pidx[buf][w][lane];
+            }
+            buf ^= 1;
+            tournament<4>(mv, mi);
+            const double sstar = mv[0];
+            int arg = mi[0];
+            double M = __dadd_rn(sstar, e1);
+            const long long bits = __double_as_longlong(sstar);
+            const double pred = __longlong_as_double(bits - ((bits >> 63) | 1));
+            const bool odd = (sstar == 0.0) | !(fabs(sstar) < CUDART_INF);
+            const bool slow = (lane < K) & (odd | (__dadd_rn(pred, e1) == M));
+            if (__builtin_expect(__any_sync(FULL, slow), 0)) {
+                const ScanResult r = viterbi_exact_scan(&xo[warp][0], LA + lane, KP, K4, e1);
+                M = r.best;
+                arg = r.arg;
+            }
+            om = M;
+            __syncwarp();                      // everyone in this warp has read xo (exact scan)
+            xo[warp][lane] = om;
+            __syncwarp();
+            e1 = e2;
+            e2 = e3;
+            if (warp == (s32 & 3)) *bpt = (uint8_t)arg;      // the four warps take turns
+            bpt += KP;
+        };
+        int64_t t0 = 0;
+        for (; t0 + 32 < T; t0 += 32) {
+#pragma unroll 4
+            for (int s32 = 0; s32 < 32; ++s32) column(s32, t0);
+            vcur = vnxt;
+            vnxt = st.load(t0 + 64, lane);
+        }
+#pragma unroll 1
+        for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32, t0);
+        if (warp == 0) {
+            // first argmax of omega_{T-1}
+            double best = (lane < K) ? om : -CUDART_INF;
+            int bidx = (lane < K) ? lane : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int oi = __shfl_xor_sync(FULL, bidx, o);
+                if (oi != 0x7fffffff && (bidx == 0x7fffffff || ob > best || (ob == best && oi < bidx))) {
+                    best = ob; bidx = oi;
+                }
+            }
+            if (lane == 0) final_state[blk] = bidx;
+        }
+        __syncthreads();
     }
 }
 

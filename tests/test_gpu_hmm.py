@@ -193,3 +193,51 @@ def test_reference_style_wrappers(engine):
         assert vit[i].dtype == np.float64 and np.array_equal(vit[i], g[f"vit_{i}"])
         assert post[i].shape == g[f"post_{i}"].shape
         assert np.abs(post[i] - g[f"post_{i}"]).max() <= POST_ATOL
+
+
+@pytest.mark.parametrize("one_warp", [False, True])
+def test_viterbi_kernel_variants_agree(engine, one_warp, monkeypatch):
+    """The four-warps-per-chain sweep (few chains) and the one-warp-per-chain sweep
+    (many chains) are both bit-exact against the oracle, on near-tie-heavy data
+    (t_A == t_B makes topologies 2 and 3 exchangeable)."""
+    if one_warp:
+        monkeypatch.setenv("ITR_VITERBI_1WARP", "1")
+    m = golden("model_3_3_example.npz")
+    a, b, pi = m["a"], m["b"], m["pi"]
+    rng = np.random.default_rng(99)
+    V_lst = [ho.sample_block(a, b, pi, T, rng, p_n=0.02) for T in (20000, 1, 257, 5000, 31)]
+    engine.load_blocks(V_lst)
+    engine.set_model(a, b, pi)
+    LA, LE, om0 = _tables(a, b, pi, V_lst)
+    path = engine.split(engine.viterbi(LA, LE, om0))
+    for p, r in zip(path, hoc.viterbi_blocks(LA, LE, om0, V_lst)):
+        assert np.array_equal(p, r)
+
+
+def test_many_blocks_and_async_overlap(engine):
+    """700 short blocks (one-warp sweep, several chains per warp through the work queue)
+    and the asynchronous mode: the three recursions enqueued back to back give the
+    same results as the synchronous calls."""
+    m = golden("model_2_2_example.npz")
+    a, b, pi = m["a"], m["b"], m["pi"]
+    rng = np.random.default_rng(3)
+    V_lst = [ho.sample_block(a, b, pi, int(T), rng, p_n=0.02) for T in rng.integers(1, 400, size=700)]
+    E = ho.emission_table(b)
+    engine.load_blocks(V_lst)
+    engine.set_model(a, b, pi)
+    LA, LE, om0 = _tables(a, b, pi, V_lst)
+    engine.set_async(True)
+    try:
+        tot = np.empty(1)
+        ll = engine.loglik()
+        path = engine.viterbi(LA, LE, om0)
+        post = engine.posterior()
+        engine.sync()
+    finally:
+        engine.set_async(False)
+    ref = hoc.loglik_blocks(a, E, pi, V_lst)
+    assert abs(ll[0] - ref.sum()) <= LL_RTOL * abs(ref.sum())
+    for p, r in zip(engine.split(path), hoc.viterbi_blocks(LA, LE, om0, V_lst)):
+        assert np.array_equal(p, r)
+    for p, r in zip(engine.split(post), hoc.post_prob_blocks(a, E, pi, V_lst)):
+        assert np.abs(p - r).max() <= POST_ATOL
