@@ -8,11 +8,13 @@ Workload (BASELINE.json configs[1], "config2"): a synthetic 4-species alignment 
 10 Mb in 100 MAF blocks (lengths uniform 50-150 kb), default discretisation
 n_int_AB = n_int_ABC = 3 (K = 27 hidden states), example_config.yaml parameters,
 1 % of columns with an N.  One *step* = one pass of the hot path over that alignment:
-forward log-likelihood + Viterbi (with traceback) + posterior decoding of every
-column.  `value` = columns / second for the whole step with the alignment and model
-resident in HBM; `breakdown` gives each recursion on its own; `e2e` is the same step
-through the C ABI with host buffers (H2D of the symbols and tables, D2H of the
-log-likelihood, the Viterbi path and the posterior matrix inside the timed region).
+one objective evaluation of itrails-optimize (GPU model build + forward
+log-likelihood) + Viterbi (with traceback) + posterior decoding of every column; the
+three recursions run concurrently on their own CUDA streams.  `value` = columns /
+second for the whole step with the alignment resident in HBM; `breakdown` gives each
+recursion's own kernel time; `e2e` is the same step through the C ABI with host
+buffers (H2D of the symbols, model and tables, D2H of the log-likelihood, the Viterbi
+path and the posterior matrix inside the timed region).
 Under torchrun each rank owns its own 10 Mb alignment (weak scaling; the blocks of a
 chromosome shard with no data-path collective) and the per-rank log-likelihoods are
 summed with one NCCL all-reduce per step.
@@ -187,6 +189,7 @@ def main():
     import torch
     import itrails_b200 as itb
     from itrails_b200 import distributed as D
+    from itrails_b200 import synth
     from itrails_b200.optimizer import viterbi_tables
 
     if world > 1:
@@ -198,6 +201,7 @@ def main():
     eng = itb.Engine(local_rank)
     info = eng.device_info()
     a, b, pi, model_src = get_model(eng, n_ab, n_abc, args.model_npz)
+    params = synth.example_model_args(n_abc)[None, :]
     K = a.shape[0]
     V_lst = make_workload(args.workload, a, b, pi, rank, args.scale)
     sym, off = itb.Engine.pack_blocks(V_lst)
@@ -211,25 +215,35 @@ def main():
         torch.cuda.synchronize()
 
     # resident step -----------------------------------------------------------------
+    # One objective evaluation (GPU model build + forward log-likelihood, what
+    # itrails-optimize does per iteration) + Viterbi + posterior decoding of the
+    # resident alignment.  The three recursions are enqueued on their own streams and
+    # overlap on the device (itr_set_async); the step ends at itr_sync.
     eng.load_packed(sym, off)
-    eng.set_model(a, b, pi)
-    launches_before = None
+    rebuild = args.model_npz is None
 
     def step_resident():
-        ll = eng.loglik()
-        if world > 1:
-            ll = D.allreduce_sum(ll, local_rank)
+        if rebuild:
+            eng.build_model(params, n_ab, n_abc, fetch=False)
+        eng.set_async(True)
         eng.viterbi(log_a, log_E, omega0, fetch=False)
         eng.posterior(fetch=False)
+        ll = eng.loglik()
+        eng.sync()
+        eng.set_async(False)
+        if world > 1:
+            ll = D.allreduce_sum(ll, local_rank)
         return ll
 
+    if not rebuild:
+        eng.set_model(a, b, pi)
     for _ in range(args.warmup):
         step_resident()
     clk_samples, stop = [], threading.Event()
     th = threading.Thread(target=sample_clocks, args=(stop, clk_samples, local_rank), daemon=True)
     if rank == 0:
         th.start()
-    phases = ("loglik", "viterbi_fwd", "viterbi_trace", "post_fwd", "post_bwd", "post_combine", "post_total")
+    phases = ("model", "loglik", "viterbi_fwd", "viterbi_trace", "post_fwd", "post_bwd", "post_combine", "post_total")
     ph_ms = {p: 0.0 for p in phases}
     barrier()
     launches_before = eng.launch_count
@@ -237,7 +251,7 @@ def main():
     for _ in range(args.steps):
         ll = step_resident()
         for p in phases:
-            ph_ms[p] += eng.phase_ms(p)
+            ph_ms[p] += max(eng.phase_ms(p), 0.0)
     barrier()
     dt = time.perf_counter() - t0
     launches = eng.launch_count - launches_before
@@ -246,15 +260,18 @@ def main():
     ms_step = dt * 1e3 / args.steps
     for p in phases:
         ph_ms[p] /= args.steps
-    dev_ms = ph_ms["loglik"] + ph_ms["viterbi_fwd"] + ph_ms["viterbi_trace"] + ph_ms["post_total"]
+    dev_ms = ph_ms["model"] + max(ph_ms["loglik"], ph_ms["viterbi_fwd"] + ph_ms["viterbi_trace"], ph_ms["post_total"])
     total_cols = float(D.allreduce_sum(np.array([float(ncol)]), local_rank)[0])
     value = total_cols / (ms_step * 1e-3)
 
     # e2e step: host buffers in, host buffers out ------------------------------------
+    # Through the C ABI with page-locked host buffers: upload of the symbols, block
+    # offsets, model matrices and Viterbi tables; download of the log-likelihood, the
+    # state path and the full posterior matrix, all inside the timed region.
     e2e = None
     if not args.no_e2e:
         pin = lambda n, dt_: torch.empty(n, dtype=dt_, pin_memory=True).numpy()
-        sym_pin = pin(len(sym), torch.uint16) if hasattr(torch, "uint16") else sym
+        sym_pin = pin(len(sym), torch.uint16)
         sym_pin[:] = sym
         path_pin = pin(ncol, torch.uint8)
         post_pin = pin(ncol * K, torch.float64).reshape(ncol, K)
@@ -262,11 +279,14 @@ def main():
         def step_e2e():
             eng.load_packed(sym_pin, off)
             eng.set_model(a, b, pi)
+            eng.set_async(True)
+            eng.posterior(out=post_pin)          # largest download first: it overlaps the rest
+            eng.viterbi(log_a, log_E, omega0, out=path_pin)
             ll = eng.loglik()
+            eng.sync()
+            eng.set_async(False)
             if world > 1:
                 ll = D.allreduce_sum(ll, local_rank)
-            eng.viterbi(log_a, log_E, omega0, out=path_pin)
-            eng.posterior(out=post_pin)
             return ll
 
         step_e2e()
@@ -296,13 +316,21 @@ def main():
     alg_flops = {"loglik": 2 * K * K + 3 * K, "viterbi_fwd": 3 * K * K, "viterbi_trace": 0,
                  "post_fwd": 2 * K * K + 3 * K, "post_bwd": 2 * K * K + 3 * K, "post_combine": 3 * K}
     dom_s = ph_ms[dom] * 1e-3
-    fp64_peak = eng.fp64_peak_tflops() if hasattr(eng, "fp64_peak_tflops") else None
+    prof = {}
+    pf = os.path.join(ROOT, "profiles", "measured_r1.json")
+    if os.path.exists(pf):
+        prof = json.load(open(pf))
+    fp64_peak = prof.get("fp64_tflops")            # DFMA/DMMA issue peak measured by tools/ubench.cu
+    traffic = (prof.get("dram_bytes_per_launch") or {}).get(dom) if args.workload == "config2" and args.scale == 1.0 else None
     roof = {"kernel": dom, "bound": "hbm", "achieved": alg_bytes[dom] * ncol / dom_s / 1e9, "peak": hbm_peak,
-            "unit": "GB/s", "peak_source": peak_src, "traffic": None}
+            "unit": "GB/s", "peak_source": peak_src, "traffic": traffic,
+            "algorithmic_bytes_per_launch": alg_bytes[dom] * ncol}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["fp64"] = {"achieved": alg_flops[dom] * ncol / dom_s / 1e12, "unit": "TFLOP/s", "peak": fp64_peak,
                     "frac": (alg_flops[dom] * ncol / dom_s / 1e12 / fp64_peak) if fp64_peak else None,
-                    "note": "the recursions are FP64-issue / dependent-chain bound, not HBM bound (SURVEY §8d)"}
+                    "note": "the recursions are dependent chains of FP64 add/compare (one chain per alignment block); "
+                            "with 100 blocks they are bound by per-column latency, not by HBM or FP64 throughput "
+                            "(DESIGN.md, SURVEY 8d)"}
 
     # CPU baseline (oracle port) on a bounded sample ---------------------------------------
     cpu = None

@@ -70,6 +70,30 @@ int itr_load_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *block_offs
 int itr_load_blocks_i64(itr_ctx *ctx, const int64_t *sym, const int64_t *block_offsets,
                         int64_t n_blocks);
 
+/* ---- MAF ingest (host only; needs no GPU) ------------------------------------------
+ * Replaces maf_parser (read_data.py:94-117) and parse_coordinates (read_data.py:146-220).
+ * species: the four names in the reference's sp_lst order (A, B sister; C; D outgroup);
+ * ref: species whose coordinates polarise the columns, or NULL for symbols only;
+ * n_threads <= 0 uses every host core.  On success *out owns:
+ *   symbols      uint16 observed-state indices of every kept block back to back
+ *                (kept = all four species present), with num_blocks + 1 offsets — exactly
+ *                the arguments of itr_load_blocks;
+ *   coordinates  (ref != NULL) int64 per column of every block whose rows hold exactly four
+ *                listed species, -9 at gaps / when ref is absent, with their own offsets.
+ * A character outside A,C,G,T,N,- (any case) in a kept block is an error, as
+ * list.index raises in the reference.  err (nullable) receives the message. */
+typedef struct itr_maf itr_maf;
+int itr_maf_read(const char *path, const char *const species[4], const char *ref, int n_threads,
+                 itr_maf **out, char *err, int err_cap);
+void itr_maf_free(itr_maf *m);
+int64_t itr_maf_num_blocks(const itr_maf *m);
+int64_t itr_maf_num_columns(const itr_maf *m);
+const uint16_t *itr_maf_symbols(const itr_maf *m);
+const int64_t *itr_maf_offsets(const itr_maf *m);
+int64_t itr_maf_num_coord_blocks(const itr_maf *m);
+const int64_t *itr_maf_coordinates(const itr_maf *m);
+const int64_t *itr_maf_coord_offsets(const itr_maf *m);
+
 /* ---- model -----------------------------------------------------------------------
  * Accepts (a, b, pi) as returned by the reference's trans_emiss_calc
  * (get_trans_emiss.py:8-170): a is n_sets x K x K, b is n_sets x K x 256,

@@ -53,6 +53,16 @@ SIGNATURES = {
     "itr_posterior_fetch": (ctypes.c_int, [_c_ctx, _dp]),
     "itr_set_async": (ctypes.c_int, [_c_ctx, ctypes.c_int]),
     "itr_sync": (ctypes.c_int, [_c_ctx]),
+    "itr_maf_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.c_int,
+                                    ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_int]),
+    "itr_maf_free": (None, [ctypes.c_void_p]),
+    "itr_maf_num_blocks": (ctypes.c_int64, [ctypes.c_void_p]),
+    "itr_maf_num_columns": (ctypes.c_int64, [ctypes.c_void_p]),
+    "itr_maf_symbols": (_u16p, [ctypes.c_void_p]),
+    "itr_maf_offsets": (_i64p, [ctypes.c_void_p]),
+    "itr_maf_num_coord_blocks": (ctypes.c_int64, [ctypes.c_void_p]),
+    "itr_maf_coordinates": (_i64p, [ctypes.c_void_p]),
+    "itr_maf_coord_offsets": (_i64p, [ctypes.c_void_p]),
     "itr_phase_ms": (ctypes.c_double, [_c_ctx, ctypes.c_int]),
     "itr_launch_count": (ctypes.c_int64, [_c_ctx]),
     "itr_total_columns": (ctypes.c_int64, [_c_ctx]),

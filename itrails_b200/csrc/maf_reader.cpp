@@ -1,0 +1,330 @@
+// maf_reader.cpp — MAF ingest for the hot path (host C++, no GPU, no Biopython).
+//
+// Replaces (reference paths relative to /root/reference/src/itrails):
+//   maf_parser          read_data.py:94-117   -> symbols (uint16, 0..624) + block offsets
+//   parse_coordinates   read_data.py:146-220  -> per-column reference coordinates / -9
+//
+// The reference goes through Biopython's AlignIO.parse(file, "maf") and resolves every
+// column with an O(625) list.index.  Here the file is mmap'ed, block boundaries are
+// found in one pass, blocks are parsed by a pool of threads, and a column is converted
+// with a 256-entry byte table and base-5 arithmetic.  Semantics kept:
+//   * a block is the run of lines after an "a" line up to a blank line / next "a" / EOF;
+//     only "s src start size strand srcSize text" rows matter; '#', track, i/e/q lines
+//     are ignored;
+//   * species = src up to the first '.'; rows of species outside the list are skipped;
+//     if a species occurs twice the last row wins (dict assignment, read_data.py:108-109);
+//   * symbols: block kept iff all four species are present (read_data.py:110);
+//     '-' counts as 'N' (:109), letters are upper-cased (:114), any other character is an
+//     error (list.index raises ValueError);
+//   * coordinates: block kept iff exactly four rows belong to listed species (:171-173,
+//     :181); forward strand starts at `start`, reverse strand at srcSize - start and runs
+//     backwards (:197-201, :213); gaps and blocks without the reference species give -9.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/itrails_b200.h"
+
+namespace {
+
+struct Row {
+    const char *src;
+    size_t src_len;
+    int64_t start, src_size;
+    int strand;
+    const char *text;
+    size_t text_len;
+};
+
+struct BlockOut {
+    bool keep_sym = false, keep_coord = false;
+    std::vector<uint16_t> sym;
+    std::vector<int64_t> coord;
+    std::string err;
+};
+
+struct Tables {
+    uint8_t digit[256];       // A,C,T,G -> 0..3 (read_data.py:13 order), N and '-' -> 4, else 255
+    uint16_t code_to_index[625];
+    Tables() {
+        memset(digit, 255, sizeof digit);
+        const char *nuc = "ACTG";
+        for (int i = 0; i < 4; ++i) {
+            digit[(unsigned char)nuc[i]] = (uint8_t)i;
+            digit[(unsigned char)(nuc[i] + 32)] = (uint8_t)i;
+        }
+        digit[(unsigned char)'N'] = digit[(unsigned char)'n'] = digit[(unsigned char)'-'] = 4;
+        int next = 256;
+        for (int a = 0; a < 5; ++a)
+            for (int b = 0; b < 5; ++b)
+                for (int c = 0; c < 5; ++c)
+                    for (int d = 0; d < 5; ++d) {
+                        const int code = ((a * 5 + b) * 5 + c) * 5 + d;
+                        if (a < 4 && b < 4 && c < 4 && d < 4) code_to_index[code] = (uint16_t)(64 * a + 16 * b + 4 * c + d);
+                        else code_to_index[code] = (uint16_t)next++;
+                    }
+    }
+};
+const Tables TAB;
+
+inline const char *skip_ws(const char *p, const char *e) {
+    while (p < e && (*p == ' ' || *p == '\t')) ++p;
+    return p;
+}
+inline const char *skip_tok(const char *p, const char *e) {
+    while (p < e && *p != ' ' && *p != '\t' && *p != '\r') ++p;
+    return p;
+}
+bool parse_i64(const char *b, const char *e, int64_t *out) {
+    if (b == e) return false;
+    int64_t v = 0;
+    for (const char *p = b; p < e; ++p) {
+        if (*p < '0' || *p > '9') return false;
+        v = v * 10 + (*p - '0');
+    }
+    *out = v;
+    return true;
+}
+
+// Parses the "s" rows of one block [b, e).
+bool parse_rows(const char *b, const char *e, std::vector<Row> &rows, std::string &err) {
+    rows.clear();
+    const char *p = b;
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        const char *le = nl ? nl : e;
+        const char *q = skip_ws(p, le);
+        if (q < le && *q == 's' && q + 1 < le && (q[1] == ' ' || q[1] == '\t')) {
+            const char *f[7], *g[7];
+            int n = 0;
+            const char *t = q;
+            while (n < 7) {
+                t = skip_ws(t, le);
+                if (t >= le || *t == '\r') break;
+                f[n] = t;
+                t = skip_tok(t, le);
+                g[n] = t;
+                ++n;
+            }
+            const char *rest = skip_ws(t, le);
+            if (n != 7 || (rest < le && *rest != '\r')) {
+                err = "malformed MAF sequence line: " + std::string(q, std::min<size_t>(60, le - q));
+                return false;
+            }
+            Row r{};
+            r.src = f[1];
+            r.src_len = g[1] - f[1];
+            if (!parse_i64(f[2], g[2], &r.start) || !parse_i64(f[5], g[5], &r.src_size) || g[4] - f[4] != 1 ||
+                (*f[4] != '+' && *f[4] != '-')) {
+                err = "malformed MAF sequence line: " + std::string(q, std::min<size_t>(60, le - q));
+                return false;
+            }
+            r.strand = *f[4] == '+' ? 1 : -1;
+            r.text = f[6];
+            r.text_len = g[6] - f[6];
+            rows.push_back(r);
+        }
+        p = nl ? nl + 1 : e;
+    }
+    return true;
+}
+
+inline int species_of(const Row &r, const char *const sp[4], const size_t sp_len[4]) {
+    size_t n = 0;
+    while (n < r.src_len && r.src[n] != '.') ++n;
+    for (int k = 0; k < 4; ++k)
+        if (n == sp_len[k] && memcmp(r.src, sp[k], n) == 0) return k;
+    return -1;
+}
+
+void do_block(const char *b, const char *e, const char *const sp[4], const size_t sp_len[4], const char *ref,
+              size_t ref_len, bool want_coord, BlockOut &out) {
+    std::vector<Row> rows;
+    if (!parse_rows(b, e, rows, out.err)) return;
+    if (rows.empty()) return;
+    const size_t len = rows[0].text_len;
+    for (const Row &r : rows)
+        if (r.text_len != len) {
+            out.err = "sequences in a MAF block must have equal length";
+            return;
+        }
+    const Row *pick[4] = {nullptr, nullptr, nullptr, nullptr};
+    const Row *ref_row = nullptr;
+    int acc = 0;
+    for (const Row &r : rows) {
+        const int k = species_of(r, sp, sp_len);
+        if (k >= 0) {
+            pick[k] = &r;
+            ++acc;
+        }
+        if (want_coord) {
+            size_t n = 0;
+            while (n < r.src_len && r.src[n] != '.') ++n;
+            if (n == ref_len && memcmp(r.src, ref, n) == 0) ref_row = &r;
+        }
+    }
+    if (pick[0] && pick[1] && pick[2] && pick[3]) {
+        out.keep_sym = true;
+        out.sym.resize(len);
+        for (size_t i = 0; i < len; ++i) {
+            int code = 0;
+            for (int k = 0; k < 4; ++k) {
+                const uint8_t d = TAB.digit[(unsigned char)pick[k]->text[i]];
+                if (d == 255) {
+                    out.err = std::string("'") + pick[k]->text[i] + "' is not a valid nucleotide in a MAF column";
+                    return;
+                }
+                code = code * 5 + d;
+            }
+            out.sym[i] = TAB.code_to_index[code];
+        }
+    }
+    if (want_coord && acc == 4) {
+        out.keep_coord = true;
+        out.coord.assign(len, -9);
+        if (ref_row) {
+            int64_t st = ref_row->strand == 1 ? ref_row->start : ref_row->src_size - ref_row->start;
+            for (size_t i = 0; i < len; ++i)
+                if (ref_row->text[i] != '-') {
+                    out.coord[i] = st;
+                    st += ref_row->strand;
+                }
+        }
+    }
+}
+
+}  // namespace
+
+struct itr_maf {
+    std::vector<uint16_t> sym;
+    std::vector<int64_t> off{0};
+    std::vector<int64_t> coord;
+    std::vector<int64_t> coord_off{0};
+    bool has_coord = false;
+};
+
+static int set_err(char *err, int cap, const std::string &msg, int code) {
+    if (err && cap > 0) {
+        strncpy(err, msg.c_str(), cap - 1);
+        err[cap - 1] = 0;
+    }
+    return code;
+}
+
+extern "C" int itr_maf_read(const char *path, const char *const species[4], const char *ref, int n_threads,
+                            itr_maf **out, char *err, int err_cap) {
+    if (!path || !species || !out) return set_err(err, err_cap, "itr_maf_read: NULL argument", ITR_ERR_ARG);
+    *out = nullptr;
+    size_t sp_len[4];
+    for (int k = 0; k < 4; ++k) {
+        if (!species[k]) return set_err(err, err_cap, "itr_maf_read: four species names are required", ITR_ERR_ARG);
+        sp_len[k] = strlen(species[k]);
+    }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return set_err(err, err_cap, std::string("cannot open ") + path, ITR_ERR_ARG);
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        return set_err(err, err_cap, std::string("cannot stat ") + path, ITR_ERR_ARG);
+    }
+    const size_t size = (size_t)st.st_size;
+    itr_maf *m = new itr_maf();
+    m->has_coord = ref != nullptr;
+    if (size == 0) {
+        close(fd);
+        *out = m;
+        return ITR_OK;
+    }
+    const char *base = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) {
+        delete m;
+        return set_err(err, err_cap, std::string("cannot mmap ") + path, ITR_ERR_NOMEM);
+    }
+    madvise((void *)base, size, MADV_SEQUENTIAL);
+    const char *end = base + size;
+    // block boundaries: [start of the line after an "a" line, start of the next "a" line / blank line)
+    std::vector<std::pair<const char *, const char *>> blocks;
+    {
+        const char *p = base, *cur = nullptr;
+        while (p < end) {
+            const char *nl = (const char *)memchr(p, '\n', end - p);
+            const char *le = nl ? nl : end;
+            const char *q = skip_ws(p, le);
+            const bool blank = (q == le) || (*q == '\r' && q + 1 == le);
+            const bool a_line = !blank && *q == 'a' && (q + 1 == le || q[1] == ' ' || q[1] == '\t' || q[1] == '\r');
+            if (blank || a_line) {
+                if (cur) blocks.push_back({cur, p});
+                cur = a_line ? (nl ? nl + 1 : end) : nullptr;
+            }
+            p = nl ? nl + 1 : end;
+        }
+        if (cur) blocks.push_back({cur, end});
+    }
+    const size_t nb = blocks.size();
+    std::vector<BlockOut> outs(nb);
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nt, 1), (nb + 15) / 16));
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    const size_t ref_len = ref ? strlen(ref) : 0;
+    auto worker = [&]() {
+        for (;;) {
+            const size_t i0 = next.fetch_add(16);
+            if (i0 >= nb || failed.load()) break;
+            for (size_t i = i0; i < std::min(nb, i0 + 16); ++i) {
+                do_block(blocks[i].first, blocks[i].second, species, sp_len, ref, ref_len, ref != nullptr, outs[i]);
+                if (!outs[i].err.empty()) failed.store(true);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    munmap((void *)base, size);
+    for (size_t i = 0; i < nb; ++i)
+        if (!outs[i].err.empty()) {       // the first failing block in file order, like a sequential parse
+            const std::string msg = outs[i].err;
+            delete m;
+            return set_err(err, err_cap, msg, ITR_ERR_ARG);
+        }
+    size_t n_sym = 0, n_coord = 0;
+    for (const BlockOut &o : outs) {
+        if (o.keep_sym) n_sym += o.sym.size();
+        if (o.keep_coord) n_coord += o.coord.size();
+    }
+    m->sym.reserve(n_sym);
+    m->coord.reserve(n_coord);
+    for (BlockOut &o : outs) {
+        if (o.keep_sym) {
+            m->sym.insert(m->sym.end(), o.sym.begin(), o.sym.end());
+            m->off.push_back((int64_t)m->sym.size());
+        }
+        if (o.keep_coord) {
+            m->coord.insert(m->coord.end(), o.coord.begin(), o.coord.end());
+            m->coord_off.push_back((int64_t)m->coord.size());
+        }
+    }
+    *out = m;
+    return ITR_OK;
+}
+
+extern "C" void itr_maf_free(itr_maf *m) { delete m; }
+extern "C" int64_t itr_maf_num_blocks(const itr_maf *m) { return m ? (int64_t)m->off.size() - 1 : 0; }
+extern "C" int64_t itr_maf_num_columns(const itr_maf *m) { return m ? (int64_t)m->sym.size() : 0; }
+extern "C" const uint16_t *itr_maf_symbols(const itr_maf *m) { return m ? m->sym.data() : nullptr; }
+extern "C" const int64_t *itr_maf_offsets(const itr_maf *m) { return m ? m->off.data() : nullptr; }
+extern "C" int64_t itr_maf_num_coord_blocks(const itr_maf *m) { return m && m->has_coord ? (int64_t)m->coord_off.size() - 1 : 0; }
+extern "C" const int64_t *itr_maf_coordinates(const itr_maf *m) { return m && m->has_coord ? m->coord.data() : nullptr; }
+extern "C" const int64_t *itr_maf_coord_offsets(const itr_maf *m) { return m && m->has_coord ? m->coord_off.data() : nullptr; }

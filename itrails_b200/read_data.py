@@ -81,43 +81,42 @@ def order_lists():
 
 
 # ---------------------------------------------------------------------------
-# MAF parsing
+# MAF parsing (C++ reader in libitrails_b200: csrc/maf_reader.cpp)
 # ---------------------------------------------------------------------------
-_BYTE_TO_DIGIT = np.full(256, 255, dtype=np.uint8)
-for _i, _ch in enumerate(NUC):
-    _BYTE_TO_DIGIT[ord(_ch)] = _i
-    _BYTE_TO_DIGIT[ord(_ch.lower())] = _i
-_BYTE_TO_DIGIT[ord("N")] = 4
-_BYTE_TO_DIGIT[ord("n")] = 4
-_BYTE_TO_DIGIT[ord("-")] = 4          # read_data.py:109: gaps become N
+def read_maf(file, sp_lst, ref=None, n_threads=0):
+    """Parse a MAF file with the native reader.  Returns ``(sym, off, coord, coord_off)``:
+    uint16 symbols of all kept blocks back to back with their int64 offsets (the arguments
+    of ``Engine.load_packed``) and, when ``ref`` is given, int64 coordinates with their own
+    offsets (else ``None, None``)."""
+    import ctypes
 
-
-def _maf_blocks(file):
-    """Yield one list of (src, start, size, strand, srcSize, text) per ``a`` block."""
-    rows, in_block = [], False
-    with open(file, "rb") as fh:
-        for raw in fh:
-            line = raw.strip()
-            if not line:
-                if in_block:
-                    yield rows
-                rows, in_block = [], False
-                continue
-            tag = line[:1]
-            if tag == b"#":
-                continue
-            if tag == b"a":
-                if in_block:
-                    yield rows
-                rows, in_block = [], True
-            elif tag == b"s" and in_block:
-                f = line.split()
-                if len(f) != 7:
-                    raise ValueError(f"malformed MAF sequence line: {line[:60]!r}")
-                strand = 1 if f[4] == b"+" else -1
-                rows.append((f[1].decode(), int(f[2]), int(f[3]), strand, int(f[5]), f[6]))
-        if in_block:
-            yield rows
+    from . import _lib as L
+    if len(sp_lst) != 4:
+        raise ValueError("sp_lst must name four species")
+    lib = L.load()
+    names = (ctypes.c_char_p * 4)(*[s.encode() for s in sp_lst])
+    handle = ctypes.c_void_p()
+    err = ctypes.create_string_buffer(512)
+    rc = lib.itr_maf_read(str(file).encode(), names, ref.encode() if ref is not None else None,
+                          int(n_threads), ctypes.byref(handle), err, 512)
+    if rc != 0:
+        msg = err.value.decode("utf-8", "replace")
+        if "cannot open" in msg or "cannot stat" in msg:
+            raise FileNotFoundError(msg)
+        raise ValueError(msg)
+    try:
+        nb, nc = lib.itr_maf_num_blocks(handle), lib.itr_maf_num_columns(handle)
+        sym = np.ctypeslib.as_array(lib.itr_maf_symbols(handle), shape=(nc,)).copy() if nc else np.zeros(0, np.uint16)
+        off = np.ctypeslib.as_array(lib.itr_maf_offsets(handle), shape=(nb + 1,)).copy()
+        coord = coord_off = None
+        if ref is not None:
+            ncb = lib.itr_maf_num_coord_blocks(handle)
+            coord_off = np.ctypeslib.as_array(lib.itr_maf_coord_offsets(handle), shape=(ncb + 1,)).copy()
+            n = int(coord_off[-1])
+            coord = np.ctypeslib.as_array(lib.itr_maf_coordinates(handle), shape=(n,)).copy() if n else np.zeros(0, np.int64)
+    finally:
+        lib.itr_maf_free(handle)
+    return sym, off, coord, coord_off
 
 
 def maf_parser(file, sp_lst):
@@ -125,55 +124,12 @@ def maf_parser(file, sp_lst):
     block that contains all four species of ``sp_lst`` (read_data.py:94-117).
     Species = text before the first ``.`` of the source name; gaps count as ``N``;
     a character outside A,C,G,T,N,- raises ValueError (as ``list.index`` does)."""
-    if _CODE_TO_INDEX is None:
-        _build_tables()
-    total = []
-    for rows in _maf_blocks(file):
-        dct = {}
-        length = None
-        for src, _start, _size, _strand, _srcsize, text in rows:
-            if length is None:
-                length = len(text)
-            elif len(text) != length:
-                raise ValueError("sequences in a MAF block must have equal length")
-            sp = src.split(".")[0]
-            if sp in sp_lst:
-                dct[sp] = text
-        if len(dct) == 4:
-            code = np.zeros(length, dtype=np.int64)
-            for sp in sp_lst:
-                d = _BYTE_TO_DIGIT[np.frombuffer(dct[sp], dtype=np.uint8)]
-                if d.size and d.max() == 255:
-                    bad = chr(dct[sp][int(np.argmax(d == 255))])
-                    raise ValueError(f"'{bad}' is not a valid nucleotide in a MAF column")
-                code = code * 5 + d
-            total.append(_CODE_TO_INDEX[code])
-    return total
+    sym, off, _, _ = read_maf(file, sp_lst)
+    return [sym[off[i]:off[i + 1]].astype(np.int64) for i in range(len(off) - 1)]
 
 
 def parse_coordinates(file, sp_lst, ref):
     """Per kept block, the reference-species coordinate of every column, -9 at
     gaps / when the reference species is absent (read_data.py:146-220)."""
-    tot = []
-    for rows in _maf_blocks(file):
-        acc, length = 0, 0
-        hit = None
-        for src, start, _size, strand, srcsize, text in rows:
-            sp = src.split(".")[0]
-            if sp in sp_lst:
-                length = len(text)
-                acc += 1
-            if sp == ref:
-                hit = (start, strand, srcsize, text)
-        if acc != 4:
-            continue
-        if hit is None:
-            tot.append([-9] * length)
-            continue
-        start, strand, srcsize, text = hit
-        st = start if strand == 1 else srcsize - start
-        present = np.frombuffer(text, dtype=np.uint8) != ord("-")
-        coords = np.full(len(text), -9, dtype=np.int64)
-        coords[present] = st + strand * np.arange(int(present.sum()))
-        tot.append(coords.tolist())
-    return tot
+    _, _, coord, coff = read_maf(file, sp_lst, ref=ref)
+    return [coord[coff[i]:coff[i + 1]].tolist() for i in range(len(coff) - 1)]

@@ -38,6 +38,20 @@ def obs_state_names():
     return plain + rest
 
 
+def code_to_index_table():
+    """Base-5 column code (digits A,C,T,G,N = 0..4, first species most significant) ->
+    index in ``obs_state_names()``."""
+    names = obs_state_names()
+    ext = NUC + "N"
+    tab = np.zeros(625, dtype=np.int64)
+    for i, s in enumerate(names):
+        code = 0
+        for ch in s:
+            code = code * 5 + ext.index(ch)
+        tab[code] = i
+    return tab
+
+
 def order_lists():
     """``order[s]``: the N-free symbol indices symbol ``s`` marginalises over.
 

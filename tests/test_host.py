@@ -138,6 +138,55 @@ def test_maf_parser_and_coordinates(tmp_path):
         itb.maf_parser(str(bad), sp)
 
 
+def test_native_maf_reader_equals_restatement(tmp_path):
+    """C++ reader (csrc/maf_reader.cpp) vs the NumPy restatement of read_data.py:94-220
+    (oracle/maf_oracle.py) on a generated MAF with lower case, gaps, N, missing and
+    duplicated species, extra species, i/e/q lines, comments and both strands."""
+    import itrails_b200 as itb
+    import maf_oracle as mo
+    rng = np.random.default_rng(11)
+    sp = ["hg38", "panTro5", "gorGor5", "ponAbe2"]
+    extra = ["macFas5", "calJac3"]
+    lines = ["##maf version=1 scoring=none", "# generated"]
+    for blk in range(300):
+        L = int(rng.integers(1, 200))
+        lines.append(f"a score={blk}.0")
+        rows = list(sp) + [e for e in extra if rng.random() < 0.5]
+        if rng.random() < 0.15:
+            rows.remove(rows[int(rng.integers(0, 4))])          # a missing species
+        if rng.random() < 0.1:
+            rows.append(sp[int(rng.integers(0, 4))])            # a duplicated species (last wins)
+        rng.shuffle(rows)
+        for name in rows:
+            seq = "".join(rng.choice(list("ACGTacgtN-"), p=[.2, .2, .2, .2, .03, .03, .03, .03, .03, .05], size=L))
+            strand = "+" if rng.random() < 0.7 else "-"
+            start = int(rng.integers(0, 10_000))
+            lines.append(f"s {name}.chr{int(rng.integers(1, 5))} {start} {L - seq.count('-')} {strand} 100000 {seq}")
+            if rng.random() < 0.2:
+                lines.append(f"i {name}.chr1 N 0 C 0")
+        if rng.random() < 0.2:
+            lines.append("e mm9.chr1 100 20 + 5000 I")
+        lines.append("")
+    p = tmp_path / "gen.maf"
+    p.write_text("\n".join(lines) + "\n")
+    want = mo.maf_parser(str(p), sp)
+    for threads in (1, 0):
+        sym, off, coord, coff = itb.read_data.read_maf(str(p), sp, ref="panTro5", n_threads=threads)
+        assert len(off) - 1 == len(want) > 100
+        for i, w in enumerate(want):
+            assert np.array_equal(sym[off[i]:off[i + 1]], w)
+        wc = mo.parse_coordinates(str(p), sp, "panTro5")
+        assert len(coff) - 1 == len(wc)
+        for i, w in enumerate(wc):
+            assert coord[coff[i]:coff[i + 1]].tolist() == w
+    assert itb.parse_coordinates(str(p), sp, "macFas5") == mo.parse_coordinates(str(p), sp, "macFas5")
+    with pytest.raises(FileNotFoundError):
+        itb.maf_parser(str(tmp_path / "missing.maf"), sp)
+    empty = tmp_path / "empty.maf"
+    empty.write_text("")
+    assert itb.maf_parser(str(empty), sp) == []
+
+
 def test_cutpoints_match_scipy():
     from scipy.stats import expon, truncexpon
     import itrails_b200 as itb
