@@ -87,7 +87,7 @@ def loglik_wrapper(a, b, pi, V_lst):
     total = eng.loglik()
     if dist_.is_active():
         total = dist_.allreduce_sum(total, eng.device)
-    return np.float64(total[0])
+    return float(total[0])      # a Python float, as the reference's numba forward_loglik returns
 
 
 def loglik_wrapper_par(a, b, pi, V_lst):

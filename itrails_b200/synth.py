@@ -68,3 +68,23 @@ def example_model_args(n_int_ABC=3, p=None):
     cut_last = -np.log1p(-(n_int_ABC - 1) / n_int_ABC)
     t_out = t_1 + t_2 + cut_last * N_ABC + t_upper + 2 * N_ABC
     return np.array([t_1, t_1, t_1 + t_2, t_2, t_upper, t_out, N_AB, N_ABC, r])
+
+
+def write_maf(path, V_lst, species=("hg38", "panTro5", "gorGor5", "ponAbe2"), line_start=1000):
+    """Write blocks of symbol indices as a MAF file (``+`` strand, one ``a`` block per
+    array, ``N`` written as ``N``), so that ``maf_parser(path, species)`` returns
+    ``V_lst`` again."""
+    names = get_obs_state_dct()
+    lut = np.array([[ord(c) for c in n] for n in names], dtype=np.uint8)     # 625 x 4
+    with open(path, "wb") as fh:
+        fh.write(b"##maf version=1 scoring=synthetic\n")
+        pos = line_start
+        for V in V_lst:
+            cols = lut[np.asarray(V, dtype=np.int64)]                         # T x 4
+            fh.write(b"a score=0\n")
+            for k, sp in enumerate(species):
+                seq = cols[:, k].tobytes()
+                size = len(seq) - seq.count(b"-")
+                fh.write(f"s {sp}.chr1 {pos} {size} + 250000000 ".encode() + seq + b"\n")
+            fh.write(b"\n")
+            pos += len(V)

@@ -42,7 +42,7 @@ def update_best_model(best_model_yaml, optim_variables, current_optim_params, cu
     for name, value in zip(optim_variables, current_optim_params):
         params[name] = float(value) * mu if name == "r" else float(value) / mu
     data["optimized_parameters"] = params
-    data["results"]["log_likelihood"] = current_result
+    data["results"]["log_likelihood"] = float(current_result)
     data["results"]["iteration"] = iteration
     with open(best_model_yaml, "w") as fh:
         yaml.dump(data, fh)

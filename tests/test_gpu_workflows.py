@@ -1,0 +1,80 @@
+"""The three console workflows end to end on a small synthetic MAF (GPU path): files
+written, formats, and consistency with the wrapper functions."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+import hmm_oracle as ho
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+SPECIES = ["hg38", "panTro5", "gorGor5", "ponAbe2"]
+
+
+@pytest.fixture(scope="module")
+def small_maf(tmp_path_factory):
+    from itrails_b200 import synth
+    m = golden("model_2_2_example.npz")
+    rng = np.random.default_rng(8)
+    V_lst = [ho.sample_block(m["a"], m["b"], m["pi"], T, rng, p_n=0.02) for T in (4000, 2500, 1, 3000)]
+    d = tmp_path_factory.mktemp("wf")
+    path = d / "small.maf"
+    synth.write_maf(str(path), V_lst, SPECIES)
+    return str(path), V_lst, str(d)
+
+
+def test_optimize_then_decode(small_maf, engine):
+    import itrails_b200 as itb
+    from itrails_b200 import engine_cache, workflows
+    maf, V_lst, d = small_maf
+    cfg = {"fixed_parameters": {"mu": 1e-8, "t_1": 240000, "t_2": 40000, "t_upper": 745069.3855, "N_ABC": 50000},
+           "optimized_parameters": {"N_AB": [40000, 5000, 500000], "r": [2e-8, 1e-9, 1e-7]},
+           "settings": {"input_maf": None, "output_prefix": None, "n_cpu": 4, "method": "Nelder-Mead",
+                        "species_list": SPECIES, "n_int_AB": 2, "n_int_ABC": 2}}
+    cfg_path = os.path.join(d, "cfg.yaml")
+    with open(cfg_path, "w") as fh:
+        yaml.safe_dump(cfg, fh)
+    prefix = os.path.join(d, "out", "run")
+    engine_cache._ENGINE = engine            # share the session's GPU context
+    res = workflows.optimize_main([cfg_path, "--input", maf, "--output", prefix])
+    assert res.success or res.nit > 10
+    hist = list(csv.reader(open(prefix + ".optimization_history.csv")))
+    assert hist[0] == ["n_eval", "N_AB", "r", "loglik", "time"] and len(hist) > 20
+    ll = np.array([float(r[3]) for r in hist[1:]])
+    best = yaml.safe_load(open(prefix + ".best_model.yaml"))
+    assert abs(best["results"]["log_likelihood"] - ll.max()) < 1e-9 * abs(ll.max())
+    assert set(best["optimized_parameters"]) == {"N_AB", "r"}
+    assert 5000 <= best["optimized_parameters"]["N_AB"] <= 500000
+    start = yaml.safe_load(open(prefix + ".starting_params.yaml"))
+    assert start["optimized_parameters"]["r"] == [2e-8, 1e-9, 1e-7]
+    # the objective at the starting point equals the wrapper's log-likelihood
+    from itrails_b200.workflows import prepare_decode
+    dec = {"fixed_parameters": dict(cfg["fixed_parameters"], N_AB=40000, r=2e-8), "optimized_parameters": {},
+           "settings": {"n_int_AB": 2, "n_int_ABC": 2}}
+    fd, nab, nabc, _, _ = prepare_decode(dec)
+    a, b, pi, hid, _ = itb.trans_emiss_calc(fd["t_A"], fd["t_B"], fd["t_C"], fd["t_2"], fd["t_upper"], fd["t_out"],
+                                            fd["N_AB"], fd["N_ABC"], fd["r"], 2, 2)
+    assert abs(itb.loglik_wrapper(a, b, pi, V_lst) - ll[0]) <= 1e-9 * abs(ll[0])
+
+    # decoding from the best model, with reference coordinates
+    out = workflows.viterbi_main(["--config-file", prefix + ".best_model.yaml", "--input", maf,
+                                  "--output", prefix, "--reference", "hg38"])
+    rows = list(csv.reader(open(out)))
+    assert rows[0] == ["Block_idx", "position_start", "position_end", "most_likely_state"]
+    assert {int(r[0]) for r in rows[1:]} == {0, 1, 2, 3}
+    assert os.path.exists(prefix + ".hidden_states.csv")
+    hs = list(csv.reader(open(prefix + ".hidden_states.csv")))
+    assert len(hs) == 1 + 13 and hs[1][4] == "(0, 0, 0)"
+    out = workflows.posterior_main(["--config-file", prefix + ".best_model.yaml", "--input", maf, "--output", prefix])
+    assert os.path.exists(prefix + ".hidden_states_2.csv")
+    rows = list(csv.reader(open(out)))
+    assert rows[0][:3] == ["alignment_block_idx", "position_idx", "prob_state_0"] and len(rows[0]) == 2 + 13
+    assert len(rows) == 1 + sum(len(v) for v in V_lst)
+    probs = np.array(rows[1:4001], dtype=float)[:, 2:]
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-9)
+    engine_cache._ENGINE = None
+    engine_cache._LOADED = None

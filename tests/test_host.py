@@ -274,3 +274,105 @@ def test_gloo_world_size_2_allreduce(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_workflow_parameter_scaling_and_cases():
+    """prepare_optimize on the reference's example config (examples/example_config.yaml
+    values): variables, scaled starting values and bounds (workflow_optimize.py:369-405)."""
+    from itrails_b200.workflows import prepare_decode, prepare_optimize
+    cfg = {"fixed_parameters": {"mu": 1e-8},
+           "optimized_parameters": {"N_AB": [50000, 5000, 500000], "N_ABC": [50000, 5000, 500000],
+                                    "t_1": [240000, 24000, 2400000], "t_2": [40000, 4000, 400000],
+                                    "t_3": [800000, 80000, 8000000],
+                                    "t_upper": [745069.3855, 74506.9385, 7450693.8556], "r": [1e-8, 1e-9, 1e-7]},
+           "settings": {"n_int_AB": 3, "n_int_ABC": 3}}
+    names, start, bounds, fixed, case = prepare_optimize(cfg, 3, 3)
+    assert names == ["t_1", "t_2", "N_ABC", "N_AB", "r", "t_upper"] and case == frozenset(["t_1"])
+    np.testing.assert_allclose(start, [240000e-8, 40000e-8, 5e-4, 5e-4, 1.0, 745069.3855e-8])
+    np.testing.assert_allclose(bounds[4], (0.1, 10.0))
+    assert fixed == {"n_int_AB": 3, "n_int_ABC": 3}
+    # t_upper derived from t_3 when absent
+    cfg2 = {k: dict(v) for k, v in cfg.items()}
+    del cfg2["optimized_parameters"]["t_upper"]
+    with pytest.raises(ValueError, match="cannot be negative"):      # 80000 - 1.0986 * 500000 < 0
+        prepare_optimize(cfg2, 3, 3)
+    cfg2["optimized_parameters"]["N_ABC"] = [50000, 40000, 60000]
+    cfg2["optimized_parameters"]["t_3"] = [800000, 700000, 900000]
+    names2, start2, bounds2, _, _ = prepare_optimize(cfg2, 3, 3)
+    last = -np.log1p(-2 / 3)
+    assert names2[-1] == "t_upper"
+    np.testing.assert_allclose(start2[-1], (800000 - last * 50000) * 1e-8)
+    np.testing.assert_allclose(bounds2[-1], ((700000 - last * 60000) * 1e-8, (900000 - last * 40000) * 1e-8))
+    bad = {k: dict(v) for k, v in cfg.items()}
+    bad["optimized_parameters"]["t_A"] = [1, 1, 1]
+    bad["optimized_parameters"]["t_B"] = [1, 1, 1]
+    with pytest.raises(ValueError, match="Invalid combination"):
+        prepare_optimize(bad, 3, 3)
+    # decoding: a best_model-style config (scalars), equals synth.example_model_args
+    from itrails_b200 import synth
+    dec = {"fixed_parameters": {"mu": 1e-8},
+           "optimized_parameters": {"N_AB": 50000, "N_ABC": 50000, "t_1": 240000, "t_2": 40000,
+                                    "t_upper": 745069.3855, "r": 1e-8},
+           "settings": {"n_int_AB": 3, "n_int_ABC": 3}}
+    d, nAB, nABC, aAB, aABC = prepare_decode(dec)
+    want = synth.example_model_args(3)
+    got = [d[k] for k in ("t_A", "t_B", "t_C", "t_2", "t_upper", "t_out", "N_AB", "N_ABC", "r")]
+    np.testing.assert_allclose(got, want, rtol=1e-14)
+    assert len(nAB) == 4 and len(nABC) == 4 and nABC[-1] == float("inf") and aABC[0] == 280000.0
+    np.testing.assert_allclose(nAB[-1], 40000 / 50000)
+
+
+def test_viterbi_segments_match_reference_loop():
+    """Run-length writer vs a literal restatement of workflow_viterbi.py:698-743."""
+    from itrails_b200.workflows import viterbi_segments
+    rng = np.random.default_rng(2)
+
+    def ref_loop(res, coords):
+        rows = []
+        if coords is None:
+            seg, cur = 0, res[0]
+            for pos in range(1, len(res)):
+                if res[pos] != cur:
+                    rows.append((seg, pos - 1, cur))
+                    seg, cur = pos, res[pos]
+            rows.append((seg, len(res) - 1, cur))
+            return rows
+        first = next((i for i, x in enumerate(coords) if x != -9), None)
+        if first is None:
+            return rows
+        seg = cnn = coords[first]
+        cur = res[first]
+        for pos in range(first, len(res)):
+            if seg == -9:
+                seg = coords[pos]; cur = res[pos]; cnn = seg
+                continue
+            if res[pos] != cur:
+                rows.append((seg, cnn, cur))
+                seg = coords[pos]; cur = res[pos]
+            cnn = coords[pos] if coords[pos] != -9 else cnn
+        if not (seg == cnn == -9):
+            rows.append((seg, cnn, cur))
+        return rows
+
+    for trial in range(30):
+        n = int(rng.integers(1, 60))
+        res = np.repeat(rng.integers(0, 4, size=n), rng.integers(1, 5, size=n)).astype(np.float64)
+        assert viterbi_segments(res) == ref_loop(res, None)
+        coords = np.arange(100, 100 + len(res)).tolist()
+        for i in rng.integers(0, len(res), size=len(res) // 3):
+            coords[int(i)] = -9
+        assert viterbi_segments(res, coords) == ref_loop(res, coords)
+    assert viterbi_segments(np.array([1.0, 1.0]), [-9, -9]) == []
+
+
+def test_write_maf_roundtrip(tmp_path):
+    import itrails_b200 as itb
+    from itrails_b200 import synth
+    rng = np.random.default_rng(4)
+    V_lst = [rng.integers(0, 625, size=int(T)) for T in (1, 50, 333)]
+    p = tmp_path / "rt.maf"
+    synth.write_maf(str(p), V_lst)
+    back = itb.maf_parser(str(p), ["hg38", "panTro5", "gorGor5", "ponAbe2"])
+    assert len(back) == 3 and all(np.array_equal(x, y) for x, y in zip(back, V_lst))
+    co = itb.parse_coordinates(str(p), ["hg38", "panTro5", "gorGor5", "ponAbe2"], "hg38")
+    assert len(co[1]) == 50
