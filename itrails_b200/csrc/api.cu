@@ -50,7 +50,11 @@ struct itr_ctx {
     int64_t *d_chunk_off = nullptr;
     int32_t *d_chunk_blk = nullptr;
     unsigned int *d_queue = nullptr;
+    size_t cap_sym = 0, cap_off = 0, cap_order = 0, cap_chunk_off = 0, cap_chunk_blk = 0;
     std::vector<int64_t> h_off;
+    std::vector<int32_t> h_order;
+    std::vector<cudaStream_t> grp_streams;     // 2 per posterior group
+    std::vector<cudaEvent_t> grp_events;       // 2 per posterior group
 
     // model
     int n_sets = 0, K = 0, KP = 0;
@@ -181,7 +185,7 @@ extern "C" int itr_create(int device, itr_ctx **out) {
         if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
         if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
-    if ((e = cudaMalloc((void **)&ctx->d_queue, 8 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_queue, 64 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
     // symbol digit table: read_data.py:6-24 ordering
     {
         std::vector<uint16_t> dig(NSYM);
@@ -209,6 +213,8 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
         if (st) cudaStreamSynchronize(st);
     delete ctx->builder;
     if (ctx->h_ll) cudaFreeHost(ctx->h_ll);
+    for (cudaStream_t st : ctx->grp_streams) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : ctx->grp_events) cudaEventDestroy(ev);
     void *ptrs[] = {ctx->d_sym, ctx->d_off, ctx->d_order, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_queue,
                     ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
@@ -281,19 +287,15 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     for (int64_t b = 0; b < n_blocks; ++b)
         std::fill(chunk_blk.begin() + chunk_off[b], chunk_blk.begin() + chunk_off[b + 1], (int32_t)b);
 
-    for (void **p : {(void **)&ctx->d_sym, (void **)&ctx->d_off, (void **)&ctx->d_order,
-                     (void **)&ctx->d_chunk_off, (void **)&ctx->d_chunk_blk}) {
-        if (*p) cudaFree(*p);
-        *p = nullptr;
-    }
     ctx->n_blocks = ctx->n_cols = ctx->n_chunks = 0;
     ctx->have_path = ctx->have_post = false;
-    // +64 columns of slack so tile prefetches past the end stay in bounds
-    CK(cudaMalloc((void **)&ctx->d_sym, (size_t)(n_cols + 64) * sizeof(uint16_t)));
-    CK(cudaMalloc((void **)&ctx->d_off, (size_t)(n_blocks + 1) * sizeof(int64_t)));
-    CK(cudaMalloc((void **)&ctx->d_order, (size_t)n_blocks * sizeof(int32_t)));
-    CK(cudaMalloc((void **)&ctx->d_chunk_off, (size_t)(n_blocks + 1) * sizeof(int64_t)));
-    CK(cudaMalloc((void **)&ctx->d_chunk_blk, (size_t)std::max<int64_t>(n_chunks, 1) * sizeof(int32_t)));
+    // device buffers are kept across loads when they are large enough
+    // (+64 columns of slack so tile prefetches past the end stay in bounds)
+    CK(ensure(ctx->d_sym, ctx->cap_sym, (size_t)(n_cols + 64)));
+    CK(ensure(ctx->d_off, ctx->cap_off, (size_t)(n_blocks + 1)));
+    CK(ensure(ctx->d_order, ctx->cap_order, (size_t)n_blocks));
+    CK(ensure(ctx->d_chunk_off, ctx->cap_chunk_off, (size_t)(n_blocks + 1)));
+    CK(ensure(ctx->d_chunk_blk, ctx->cap_chunk_blk, (size_t)std::max<int64_t>(n_chunks, 1)));
     CK(cudaMemsetAsync(ctx->d_sym + n_cols, 0, 64 * sizeof(uint16_t), ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_sym, sym, (size_t)n_cols * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -303,6 +305,7 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     ctx->h_off.assign(off, off + n_blocks + 1);
+    ctx->h_order = order;
     ctx->n_blocks = n_blocks;
     ctx->n_cols = n_cols;
     ctx->n_chunks = n_chunks;
@@ -327,8 +330,11 @@ extern "C" int itr_load_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t 
     int rc = check_offsets(ctx, off, n_blocks);
     if (rc) return rc;
     const int64_t n = off[n_blocks];
-    for (int64_t i = 0; i < n; ++i)
-        if (sym[i] >= NSYM) return fail(ctx, ITR_ERR_ARG, "symbol %u at column %lld is outside 0..624", sym[i], (long long)i);
+    uint16_t mx = 0;
+    for (int64_t i = 0; i < n; ++i) mx = std::max(mx, sym[i]);          // vectorised by the compiler
+    if (mx >= NSYM)
+        for (int64_t i = 0; i < n; ++i)
+            if (sym[i] >= NSYM) return fail(ctx, ITR_ERR_ARG, "symbol %u at column %lld is outside 0..624", sym[i], (long long)i);
     return install_blocks(ctx, sym, off, n_blocks);
 }
 
@@ -359,6 +365,7 @@ static int quiesce(itr_ctx *ctx) {
     finish_loglik(ctx);
     return ITR_OK;
 }
+// (the posterior group streams always join s_post before a call returns control)
 
 // Installs a model whose raw arrays are already on the device.
 int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, const double *d_b, const double *d_pi) {
@@ -514,11 +521,16 @@ static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
 #endif
 
 template <int MODE>
-static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha, cudaStream_t st, int slot) {
+static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha, cudaStream_t st, int slot,
+                           int first = 0, int count = -1) {
     const int K = ctx->K, KP = ctx->KP;
-    const Geometry g = geometry(ctx, (int64_t)n_sets * ctx->n_blocks, 16);
+    ChainSet cs = chain_set(ctx, n_sets, slot);
+    if (count >= 0) {           // a contiguous range of the longest-first order
+        cs.order += first;
+        cs.n_blocks = count;
+    }
+    const Geometry g = geometry(ctx, (int64_t)n_sets * cs.n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    const ChainSet cs = chain_set(ctx, n_sets, slot);
     cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
 #define FWD_REG(KT) \
     forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
@@ -530,11 +542,15 @@ static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alp
     ctx->launches += 1;
 }
 
-static void launch_backward(itr_ctx *ctx, cudaStream_t st) {
+static void launch_backward(itr_ctx *ctx, cudaStream_t st, int slot = 1, int first = 0, int count = -1) {
     const int K = ctx->K, KP = ctx->KP;
-    const Geometry g = geometry(ctx, ctx->n_blocks, 16);
+    ChainSet cs = chain_set(ctx, 1, slot);
+    if (count >= 0) {
+        cs.order += first;
+        cs.n_blocks = count;
+    }
+    const Geometry g = geometry(ctx, cs.n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    const ChainSet cs = chain_set(ctx, 1, 1);
     cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
 #define BWD_REG(KT) backward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_Et, K, ctx->d_beta)
 #define BWD_GEN(NS) backward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_Et, K, ctx->d_beta)
@@ -552,6 +568,21 @@ static cudaError_t launch_combine_t(itr_ctx *ctx, cudaStream_t st) {
     posterior_combine_kernel<COLS><<<blocks_for((size_t)ctx->n_cols, COLS), COLS, sh, st>>>(ctx->d_post, ctx->d_beta, ctx->K, ctx->n_cols);
     ctx->launches += 1;
     return cudaSuccess;
+}
+template <int COLS>
+static cudaError_t launch_combine_blocks_t(itr_ctx *ctx, cudaStream_t st, int first, int count, int64_t max_T) {
+    const size_t sh = (size_t)COLS * ctx->K * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(posterior_combine_blocks_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    posterior_combine_blocks_kernel<COLS><<<dim3(blocks_for((size_t)max_T, COLS), count), COLS, sh, st>>>(
+        ctx->d_post, ctx->d_beta, ctx->K, ctx->d_off, ctx->d_order + first);
+    ctx->launches += 1;
+    return cudaSuccess;
+}
+static cudaError_t launch_combine_blocks(itr_ctx *ctx, cudaStream_t st, int first, int count, int64_t max_T) {
+    if (ctx->K <= 40) return launch_combine_blocks_t<256>(ctx, st, first, count, max_T);
+    if (ctx->K <= 160) return launch_combine_blocks_t<64>(ctx, st, first, count, max_T);
+    return launch_combine_blocks_t<32>(ctx, st, first, count, max_T);
 }
 static cudaError_t launch_combine(itr_ctx *ctx, cudaStream_t st) {
     if (ctx->K <= 40) return launch_combine_t<256>(ctx, st);
@@ -765,6 +796,65 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
     // forward (alpha -> d_post) on the posterior stream, backward (beta -> d_beta) on
     // the second stream, concurrently; then the combine on the posterior stream.
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    const int n_groups = (post && ctx->n_blocks >= 16 && !getenv("ITR_POST_ONE_GROUP")) ? 8 : 1;
+    if (n_groups > 1) {
+        // Blocks are independent: run them in groups of similar length (contiguous ranges
+        // of the longest-first order), each group on its own pair of streams, and start
+        // the download of a group as soon as it is done — the PCIe transfer of the short
+        // blocks overlaps the recursions of the long ones.
+        while ((int)ctx->grp_streams.size() < 2 * n_groups) {
+            cudaStream_t s2 = nullptr;
+            cudaEvent_t e2 = nullptr;
+            CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            ctx->grp_streams.push_back(s2);
+            CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            ctx->grp_events.push_back(e2);
+        }
+        phase_begin(ctx, ITR_PH_POST_TOTAL, st);
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        const int nb = (int)ctx->n_blocks;
+        for (int g = n_groups - 1; g >= 0; --g) {          // shortest group first
+            const int first = (int)((int64_t)nb * g / n_groups), last = (int)((int64_t)nb * (g + 1) / n_groups);
+            const int count = last - first;
+            if (count <= 0) continue;
+            cudaStream_t sa = ctx->grp_streams[2 * g], sb = ctx->grp_streams[2 * g + 1];
+            cudaEvent_t ea = ctx->grp_events[2 * g], eb = ctx->grp_events[2 * g + 1];
+            CK(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+            CK(cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
+            if (g == 0) phase_begin(ctx, ITR_PH_POST_BWD, sb);
+            launch_backward(ctx, sb, 8 + 2 * g, first, count);
+            if (g == 0) phase_end(ctx, ITR_PH_POST_BWD, sb);
+            CK(cudaEventRecord(eb, sb));
+            if (g == 0) phase_begin(ctx, ITR_PH_POST_FWD, sa);
+            launch_forward<1>(ctx, 1, nullptr, ctx->d_post, sa, 9 + 2 * g, first, count);
+            if (g == 0) phase_end(ctx, ITR_PH_POST_FWD, sa);
+            CK(cudaStreamWaitEvent(sa, eb, 0));
+            const int32_t longest = ctx->h_order[first];
+            if (g == 0) phase_begin(ctx, ITR_PH_POST_COMBINE, sa);
+            CK(launch_combine_blocks(ctx, sa, first, count, ctx->h_off[longest + 1] - ctx->h_off[longest]));
+            if (g == 0) phase_end(ctx, ITR_PH_POST_COMBINE, sa);
+        }
+        // downloads, shortest group first (issued after every kernel is enqueued, so that a
+        // pageable destination — whose copies block the host — does not delay launches)
+        for (int g = n_groups - 1; g >= 0; --g) {
+            const int first = (int)((int64_t)nb * g / n_groups), last = (int)((int64_t)nb * (g + 1) / n_groups);
+            if (last <= first) continue;
+            cudaStream_t sa = ctx->grp_streams[2 * g];
+            cudaEvent_t ea = ctx->grp_events[2 * g];
+            for (int q = first; q < last; ++q) {
+                const int32_t blk = ctx->h_order[q];
+                const size_t o = (size_t)ctx->h_off[blk] * ctx->K, len = (size_t)(ctx->h_off[blk + 1] - ctx->h_off[blk]) * ctx->K;
+                CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, sa));
+            }
+            CK(cudaEventRecord(ea, sa));
+            CK(cudaStreamWaitEvent(st, ea, 0));
+        }
+        phase_end(ctx, ITR_PH_POST_TOTAL, st);
+        CK(cudaGetLastError());
+        ctx->have_post = true;
+        if (!ctx->async) CK(cudaStreamSynchronize(st));
+        return ITR_OK;
+    }
     phase_begin(ctx, ITR_PH_POST_TOTAL, st);
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));

@@ -450,6 +450,34 @@ posterior_combine_kernel(double *__restrict__ post, const double *__restrict__ b
     for (int i = threadIdx.x; i < n; i += COLS) p[i] = sm[i] * rcp[i / K];
 }
 
+// Same, for a group of blocks (blockIdx.y indexes `order`): used when the posterior is
+// produced group by group so that the download of finished (shorter) blocks overlaps
+// the recursions of the longer ones.
+template <int COLS>
+__global__ void __launch_bounds__(COLS)
+posterior_combine_blocks_kernel(double *__restrict__ post, const double *__restrict__ beta, int K,
+                                const int64_t *__restrict__ off, const int32_t *__restrict__ order) {
+    extern __shared__ __align__(16) double sm[];
+    const int blk = order[blockIdx.y];
+    const int64_t c0 = off[blk] + (int64_t)blockIdx.x * COLS;
+    const int nc = (int)min((int64_t)COLS, off[blk + 1] - c0);
+    if (nc <= 0) return;
+    const int n = nc * K;
+    double *p = post + (size_t)c0 * K;
+    const double *b = beta + (size_t)c0 * K;
+    for (int i = threadIdx.x; i < n; i += COLS) sm[i] = p[i] * b[i];
+    __syncthreads();
+    __shared__ double rcp[COLS];
+    if ((int)threadIdx.x < nc) {
+        const double *r = sm + (size_t)threadIdx.x * K;
+        double acc = 0.0;
+        for (int j = 0; j < K; ++j) acc += r[j];
+        rcp[threadIdx.x] = 1.0 / acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += COLS) p[i] = sm[i] * rcp[i / K];
+}
+
 // ---------------------------------------------------------------------------------
 // Viterbi forward sweep (max-plus), bit-exact recipe:
 //   m_ij = (omega_i + LA_ij) + LE_j ; prev_j = first argmax_i ; omega_j = max_i
