@@ -720,21 +720,43 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
 // add + exactness check exactly as in viterbi_forward_kernel).  Same results bit for
 // bit; ~2.5x shorter column latency.
 // ---------------------------------------------------------------------------------
+// Cold path of viterbi_forward4_kernel (about once per binade crossing of omega): the
+// exactness check of the previous column fired.  Every warp redoes that column with
+// the literal two-add scan from omega_{t-2} (`prev`), overwrites its copy of
+// omega_{t-1} (`cur`) and the backpointer row.  Kept out of line so that the hot loop
+// stays straight-line code.
+__device__ __noinline__ void viterbi4_repair(const double *prev, double *cur, const double *lac, int K4,
+                                             double le, uint8_t *row, int *slow_flag) {
+    __syncthreads();                       // everyone has seen the flag
+    if (threadIdx.x == 0) *slow_flag = 0;
+    const ScanResult r = viterbi_exact_scan(prev, lac, 32, K4, le);
+    cur[threadIdx.x & 31] = r.best;
+    if (threadIdx.x < 32) *row = (uint8_t)r.arg;
+    __syncwarp();
+}
+
+__device__ __forceinline__ double2 lds_f64x2(const double *p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 template <int CPW>
 __global__ void __launch_bounds__(128)
 viterbi_forward4_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                         const double *__restrict__ OM0, int K,
                         uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
     constexpr int KP = 32;
-    __shared__ __align__(16) double xo[4][KP];          // each warp's private copy of omega
+    __shared__ __align__(16) double xo[4][2][KP];       // each warp's private copies of omega_{t-1}, omega_t
     __shared__ __align__(16) double pv[2][4][KP];       // partial maxima
     __shared__ int pidx[2][4][KP];                      // partial arg-maxima
-    __shared__ int chain_s;
+    __shared__ int chain_s, slow_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_chains = cs.n_blocks;
     const int K4 = (K + 3) & ~3;
     const double *etl = LEt + lane;
     const int i0 = warp * CPW;
+    if (threadIdx.x == 0) slow_flag = 0;
 
     // rows i0 .. i0+CPW-1 of log a, column `lane`
     double la[CPW];
@@ -752,70 +774,82 @@ viterbi_forward4_kernel(ChainSet cs, const double *__restrict__ LA, const double
         const SymTile st{cs.sym + beg, T};
         uint8_t *bpl = bp + (size_t)beg * KP + lane;
 
-        double om = __ldg(OM0 + (size_t)blk * KP + lane);
         unsigned vcur = st.load(0, lane);
         unsigned vnxt = st.load(32, lane);
-        double e1, e2;
+        double e1, e2, e0 = 0.0;                 // e0: emission row of the column just produced
         {
             const unsigned v1 = __shfl_sync(FULL, vcur, 1), v2 = __shfl_sync(FULL, vcur, 2);
             e1 = __ldg(etl + v1 * KP);
             e2 = __ldg(etl + v2 * KP);
         }
-        xo[warp][lane] = om;
+        int cur = 0;                             // xo[warp][cur] holds the newest omega
+        xo[warp][0][lane] = __ldg(OM0 + (size_t)blk * KP + lane);
         __syncwarp();
         unsigned vpre = tile_symbol(vcur, vnxt, 3);      // symbol of the column two ahead
         uint8_t *bpt = bpl + KP;                          // row of column t = 1
         int buf = 0;
+        // exactness check of the previous column, evaluated lazily: f(pred(s*)) == f(s*)?
+        double chk_s = -1.0, chk_m = 0.0;        // s* and M of the previous column (e0 is its emission)
+
         auto column = [&](int s32, int64_t t0) {
-            // ---- phase A: this warp's CPW predecessors
-            const double2 *x2 = reinterpret_cast<const double2 *>(&xo[warp][i0]);
-            double sv[CPW];
-            int ix[CPW];
+            double mv[4];
+            int mi[4];
+            for (;;) {
+                // ---- phase A: this warp's CPW predecessors of the column after xo[warp][cur]
+                const double *xw = &xo[warp][cur][i0];
+                double2 px[CPW / 2];
 #pragma unroll
-            for (int q = 0; q < CPW; q += 2) {
-                const double2 p = x2[q / 2];
-                sv[q] = __dadd_rn(p.x, la[q]);
-                sv[q + 1] = __dadd_rn(p.y, la[q + 1]);
-                ix[q] = i0 + q;
-                ix[q + 1] = i0 + q + 1;
+                for (int q = 0; q < CPW / 2; ++q) px[q] = lds_f64x2(xw + 2 * q);
+                // the previous column's check, off the dependent chain (its inputs are old)
+                {
+                    const long long bits = __double_as_longlong(chk_s);
+                    const double pred = __longlong_as_double(bits - ((bits >> 63) | 1));
+                    const bool odd = (chk_s == 0.0) | !(fabs(chk_s) < CUDART_INF);
+                    if ((lane < K) & (odd | (__dadd_rn(pred, e0) == chk_m))) slow_flag = 1;
+                }
+                double sv[CPW];
+                int ix[CPW];
+#pragma unroll
+                for (int q = 0; q < CPW; q += 2) {
+                    sv[q] = __dadd_rn(px[q / 2].x, la[q]);
+                    sv[q + 1] = __dadd_rn(px[q / 2].y, la[q + 1]);
+                    ix[q] = i0 + q;
+                    ix[q + 1] = i0 + q + 1;
+                }
+                tournament<CPW>(sv, ix);
+                pv[buf][warp][lane] = sv[0];
+                pidx[buf][warp][lane] = ix[0];
+                __syncthreads();
+                // ---- phase B: the four partials (ascending i ranges) and the check flag
+                const int sf = slow_flag;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    mv[w] = pv[buf][w][lane];
+                    mi[w] = pidx[buf][w][lane];
+                }
+                if (__builtin_expect(sf == 0, 1)) break;
+                viterbi4_repair(&xo[warp][cur ^ 1][0], &xo[warp][cur][0], LA + lane, K4, e0, bpt - KP, &slow_flag);
+                chk_s = -1.0;                     // resolved (a finite negative value never fires)
+                chk_m = 0.0;
+                __syncthreads();                  // partial buffers may be rewritten
             }
             // emission row two columns ahead; its symbol was shuffled out one column ago
             const double e3 = __ldg(etl + vpre * KP);
             vpre = tile_symbol(vcur, vnxt, s32 + 4);
-            tournament<CPW>(sv, ix);
-            pv[buf][warp][lane] = sv[0];
-            pidx[buf][warp][lane] = ix[0];
-            __syncthreads();
-            // ---- phase B: merge the four partials (ascending i ranges)
-            double mv[4];
-            int mi[4];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                mv[w] = pv[buf][w][lane];
-                mi[w] = pidx[buf][w][lane];
-            }
             buf ^= 1;
             tournament<4>(mv, mi);
             const double sstar = mv[0];
-            int arg = mi[0];
-            double M = __dadd_rn(sstar, e1);
-            const long long bits = __double_as_longlong(sstar);
-            const double pred = __longlong_as_double(bits - ((bits >> 63) | 1));
-            const bool odd = (sstar == 0.0) | !(fabs(sstar) < CUDART_INF);
-            const bool slow = (lane < K) & (odd | (__dadd_rn(pred, e1) == M));
-            if (__builtin_expect(__any_sync(FULL, slow), 0)) {
-                const ScanResult r = viterbi_exact_scan(&xo[warp][0], LA + lane, KP, K4, e1);
-                M = r.best;
-                arg = r.arg;
-            }
-            om = M;
-            __syncwarp();                      // everyone in this warp has read xo (exact scan)
-            xo[warp][lane] = om;
+            const double M = __dadd_rn(sstar, e1);
+            cur ^= 1;
+            xo[warp][cur][lane] = M;
             __syncwarp();
+            if (warp == (s32 & 3)) *bpt = (uint8_t)mi[0];    // the four warps take turns
+            bpt += KP;
+            chk_s = sstar;
+            chk_m = M;
+            e0 = e1;
             e1 = e2;
             e2 = e3;
-            if (warp == (s32 & 3)) *bpt = (uint8_t)arg;      // the four warps take turns
-            bpt += KP;
         };
         int64_t t0 = 0;
         for (; t0 + 32 < T; t0 += 32) {
@@ -826,8 +860,18 @@ viterbi_forward4_kernel(ChainSet cs, const double *__restrict__ LA, const double
         }
 #pragma unroll 1
         for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32, t0);
+        {   // check of the last column
+            const long long bits = __double_as_longlong(chk_s);
+            const double pred = __longlong_as_double(bits - ((bits >> 63) | 1));
+            const bool odd = (chk_s == 0.0) | !(fabs(chk_s) < CUDART_INF);
+            const bool slow = (lane < K) & (odd | (__dadd_rn(pred, e0) == chk_m));
+            if (__syncthreads_or(slow) && T > 1)
+                viterbi4_repair(&xo[warp][cur ^ 1][0], &xo[warp][cur][0], LA + lane, K4, e0, bpt - KP, &slow_flag);
+            __syncthreads();
+        }
         if (warp == 0) {
             // first argmax of omega_{T-1}
+            const double om = xo[0][cur][lane];
             double best = (lane < K) ? om : -CUDART_INF;
             int bidx = (lane < K) ? lane : 0x7fffffff;
 #pragma unroll
