@@ -63,6 +63,15 @@ struct itr_ctx {
     uint16_t *d_digits = nullptr;
     size_t cap_A = 0, cap_PI = 0, cap_Et = 0, cap_braw = 0;
 
+    // run compression of the forward log-likelihood (hmm_kernels.cuh)
+    int32_t *d_rep = nullptr, *d_sP = nullptr;
+    unsigned long long *d_hist = nullptr;
+    uint8_t *d_isrun = nullptr;
+    long long *d_runinfo = nullptr;
+    double *d_P = nullptr, *d_ebar = nullptr;
+    size_t cap_P = 0, cap_sP = 0, cap_ebar = 0;
+    bool hist_valid = false, runs_valid = false, use_runs = false, use_runs_known = false;
+
     // log-likelihood
     double *d_ll = nullptr;
     size_t cap_ll = 0;
@@ -218,7 +227,8 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
     void *ptrs[] = {ctx->d_sym, ctx->d_off, ctx->d_order, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_queue,
                     ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
-                    ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta};
+                    ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
+                    ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -306,6 +316,7 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     ctx->h_off.assign(off, off + n_blocks + 1);
     ctx->h_order = order;
+    ctx->hist_valid = ctx->runs_valid = ctx->use_runs_known = false;
     ctx->n_blocks = n_blocks;
     ctx->n_cols = n_cols;
     ctx->n_chunks = n_chunks;
@@ -387,6 +398,7 @@ int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, con
     ctx->K = K;
     ctx->KP = KP;
     ctx->have_path = ctx->have_post = false;
+    ctx->runs_valid = false;
     return ITR_OK;
 }
 
@@ -620,6 +632,72 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
 #undef VIT_GEN
 }
 
+// Tables of the run-compressed forward sweep for the resident blocks + model; decides
+// once per alignment (one 16-byte read-back) whether a dominant emission class exists.
+static int prepare_runs(itr_ctx *ctx, cudaStream_t st) {
+    if (ctx->K > 32 || getenv("ITR_NO_RUNS")) {
+        ctx->use_runs = false;
+        return ITR_OK;
+    }
+    if (ctx->use_runs_known && !ctx->use_runs) return ITR_OK;
+    if (!ctx->d_rep) {
+        CK(cudaMalloc((void **)&ctx->d_rep, NSYM * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&ctx->d_hist, NSYM * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&ctx->d_isrun, 640));
+        CK(cudaMalloc((void **)&ctx->d_runinfo, 2 * sizeof(long long)));
+    }
+    if (!ctx->hist_valid) {
+        CK(cudaMemsetAsync(ctx->d_hist, 0, NSYM * sizeof(unsigned long long), st));
+        symbol_hist_kernel<<<std::min<unsigned>(blocks_for((size_t)ctx->n_cols, 256), 4u * ctx->prop.multiProcessorCount), 256, 0, st>>>(
+            ctx->d_sym, ctx->n_cols, ctx->d_hist);
+        ctx->launches += 1;
+        ctx->hist_valid = true;
+    }
+    if (!ctx->runs_valid) {
+        const int KP = ctx->KP;
+        CK(ensure(ctx->d_P, ctx->cap_P, (size_t)ctx->n_sets * RUN_POWERS * KP * KP));
+        CK(ensure(ctx->d_sP, ctx->cap_sP, (size_t)ctx->n_sets * RUN_POWERS));
+        CK(ensure(ctx->d_ebar, ctx->cap_ebar, (size_t)ctx->n_sets * KP));
+        symbol_class_kernel<<<1, 640, 0, st>>>(ctx->d_Et, ctx->K, KP, ctx->n_sets, 1e-12, ctx->d_rep);
+        pick_run_class_kernel<<<1, 640, 0, st>>>(ctx->d_hist, ctx->d_rep, ctx->d_isrun, ctx->d_runinfo);
+        run_power_kernel<<<ctx->n_sets, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, ctx->d_P, ctx->d_sP, ctx->d_ebar);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        ctx->runs_valid = true;
+    }
+    if (!ctx->use_runs_known) {
+        long long info[2] = {0, 0};
+        CK(cudaMemcpyAsync(info, ctx->d_runinfo, sizeof info, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->use_runs = info[1] * 2 > ctx->n_cols;      // a class holding most columns
+        ctx->use_runs_known = true;
+    }
+    return ITR_OK;
+}
+
+static void launch_forward_runs(itr_ctx *ctx, double *d_ll, cudaStream_t st) {
+    const int K = ctx->K, KP = ctx->KP;
+    const ChainSet cs = chain_set(ctx, ctx->n_sets, 0);
+    const Geometry g = geometry(ctx, (int64_t)ctx->n_sets * ctx->n_blocks, 12);
+    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+#define RUN_K(KT)                                                                                        \
+    forward_runs_kernel<KT><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P, \
+                                                              ctx->d_sP, ctx->d_ebar, ctx->d_isrun, K, d_ll)
+    switch ((K + 3) / 4) {
+        case 1: RUN_K(4); break;
+        case 2: RUN_K(8); break;
+        case 3: RUN_K(12); break;
+        case 4: RUN_K(16); break;
+        case 5: RUN_K(20); break;
+        case 6: RUN_K(24); break;
+        case 7: RUN_K(28); break;
+        default: RUN_K(32); break;
+    }
+#undef RUN_K
+    ctx->launches += 1;
+}
+
 static int need_ready(itr_ctx *ctx, const char *who) {
     if (ctx->n_blocks == 0) return fail(ctx, ITR_ERR_STATE, "%s: no blocks loaded (call itr_load_blocks first)", who);
     if (ctx->K == 0) return fail(ctx, ITR_ERR_STATE, "%s: no model installed (call itr_set_model or itr_build_model first)", who);
@@ -688,8 +766,11 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
         ctx->cap_hll = n;
     }
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    rc = prepare_runs(ctx, st);
+    if (rc) return rc;
     phase_begin(ctx, ITR_PH_LOGLIK, st);
-    launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr, st, 0);
+    if (ctx->use_runs) launch_forward_runs(ctx, ctx->d_ll, st);
+    else launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr, st, 0);
     phase_end(ctx, ITR_PH_LOGLIK, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_ll, ctx->d_ll, n * sizeof(double), cudaMemcpyDeviceToHost, st));
