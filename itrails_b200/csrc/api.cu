@@ -635,10 +635,6 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
 // Tables of the run-compressed forward sweep for the resident blocks + model; decides
 // once per alignment (one 16-byte read-back) whether a dominant emission class exists.
 static int prepare_runs(itr_ctx *ctx, cudaStream_t st) {
-    if (ctx->K > 32 || getenv("ITR_NO_RUNS")) {
-        ctx->use_runs = false;
-        return ITR_OK;
-    }
     if (ctx->use_runs_known && !ctx->use_runs) return ITR_OK;
     if (!ctx->d_rep) {
         CK(cudaMalloc((void **)&ctx->d_rep, NSYM * sizeof(int32_t)));
@@ -766,10 +762,14 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
         ctx->cap_hll = n;
     }
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
-    rc = prepare_runs(ctx, st);
-    if (rc) return rc;
+    bool runs = ctx->K <= 32 && !getenv("ITR_NO_RUNS");     // (the variable is for experiments and tests)
+    if (runs) {
+        rc = prepare_runs(ctx, st);
+        if (rc) return rc;
+        runs = ctx->use_runs;
+    }
     phase_begin(ctx, ITR_PH_LOGLIK, st);
-    if (ctx->use_runs) launch_forward_runs(ctx, ctx->d_ll, st);
+    if (runs) launch_forward_runs(ctx, ctx->d_ll, st);
     else launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr, st, 0);
     phase_end(ctx, ITR_PH_LOGLIK, st);
     CK(cudaGetLastError());

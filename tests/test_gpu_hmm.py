@@ -241,3 +241,32 @@ def test_many_blocks_and_async_overlap(engine):
         assert np.array_equal(p, r)
     for p, r in zip(engine.split(post), hoc.post_prob_blocks(a, E, pi, V_lst)):
         assert np.abs(p - r).max() <= POST_ATOL
+
+
+def test_run_compressed_loglik_equals_plain_sweep(engine, monkeypatch):
+    """The run-compressed forward sweep (invariant-column runs applied as precomputed
+    powers) against the column-by-column sweep and the oracle: several parameter sets,
+    N columns, short blocks; and data without a dominant class (plain sweep is chosen)."""
+    m = golden("model_3_3_example.npz")
+    a, b, pi = m["a"], m["b"], m["pi"]
+    rng = np.random.default_rng(21)
+    m2 = golden("model_3_3_asym1.npz")
+    V_lst = [ho.sample_block(a, b, pi, T, rng, p_n=0.02) for T in (30000, 1, 2, 33, 64, 65, 4097, 12000)]
+    V_lst[4][:] = 0                      # one block that is a single run
+    engine.load_blocks(V_lst)
+    A = np.stack([a, m2["a"]]); B = np.stack([b, m2["b"]]); PI = np.stack([pi, m2["pi"]])
+    engine.set_model(A, B, PI)
+    _, pb_runs = engine.loglik(per_block=True)
+    monkeypatch.setenv("ITR_NO_RUNS", "1")
+    _, pb_plain = engine.loglik(per_block=True)
+    monkeypatch.delenv("ITR_NO_RUNS")
+    np.testing.assert_allclose(pb_runs, pb_plain, rtol=1e-12)
+    for k, (aa, bb, pp) in enumerate(((a, b, pi), (m2["a"], m2["b"], m2["pi"]))):
+        ref = hoc.loglik_blocks(aa, ho.emission_table(bb), pp, V_lst)
+        np.testing.assert_allclose(pb_runs[k], ref, rtol=LL_RTOL)
+    # uniform random symbols: no class holds half of the columns
+    V_rand = [rng.integers(0, 625, size=5000) for _ in range(3)]
+    engine.load_blocks(V_rand)
+    engine.set_model(a, b, pi)
+    _, pb = engine.loglik(per_block=True)
+    np.testing.assert_allclose(pb[0], hoc.loglik_blocks(a, ho.emission_table(b), pi, V_rand), rtol=LL_RTOL)
