@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <new>
 #include <numeric>
@@ -70,7 +71,7 @@ struct itr_ctx {
     long long *d_runinfo = nullptr;
     double *d_P = nullptr, *d_ebar = nullptr;
     size_t cap_P = 0, cap_sP = 0, cap_ebar = 0;
-    bool hist_valid = false, runs_valid = false, use_runs = false, use_runs_known = false;
+    bool runs_valid = false, use_runs = false;
 
     // log-likelihood
     double *d_ll = nullptr;
@@ -312,11 +313,27 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)n_blocks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_chunk_off, chunk_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_chunk_blk, chunk_blk.data(), (size_t)n_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // symbol histogram (model independent): decides whether the run-compressed forward
+    // sweep is worth using — are most columns covered by a handful of symbols?
+    if (!ctx->d_hist) {
+        CK(cudaMalloc((void **)&ctx->d_rep, NSYM * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&ctx->d_hist, NSYM * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&ctx->d_isrun, 640));
+        CK(cudaMalloc((void **)&ctx->d_runinfo, 2 * sizeof(long long)));
+    }
+    CK(cudaMemsetAsync(ctx->d_hist, 0, NSYM * sizeof(unsigned long long), ctx->stream));
+    symbol_hist_kernel<<<std::min<unsigned>(blocks_for((size_t)n_cols, 256), 4u * ctx->prop.multiProcessorCount), 256, 0, ctx->stream>>>(
+        ctx->d_sym, n_cols, ctx->d_hist);
+    ctx->launches += 1;
+    std::vector<unsigned long long> hist(NSYM);
+    CK(cudaMemcpyAsync(hist.data(), ctx->d_hist, NSYM * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    std::partial_sort(hist.begin(), hist.begin() + 4, hist.end(), std::greater<unsigned long long>());
+    ctx->use_runs = 2 * (hist[0] + hist[1] + hist[2] + hist[3]) > (unsigned long long)n_cols;
+    ctx->runs_valid = false;
     ctx->h_off.assign(off, off + n_blocks + 1);
     ctx->h_order = order;
-    ctx->hist_valid = ctx->runs_valid = ctx->use_runs_known = false;
     ctx->n_blocks = n_blocks;
     ctx->n_cols = n_cols;
     ctx->n_chunks = n_chunks;
@@ -632,42 +649,20 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
 #undef VIT_GEN
 }
 
-// Tables of the run-compressed forward sweep for the resident blocks + model; decides
-// once per alignment (one 16-byte read-back) whether a dominant emission class exists.
+// Tables of the run-compressed forward sweep for the resident blocks + model (three
+// small launches after a model change; nothing is read back).
 static int prepare_runs(itr_ctx *ctx, cudaStream_t st) {
-    if (ctx->use_runs_known && !ctx->use_runs) return ITR_OK;
-    if (!ctx->d_rep) {
-        CK(cudaMalloc((void **)&ctx->d_rep, NSYM * sizeof(int32_t)));
-        CK(cudaMalloc((void **)&ctx->d_hist, NSYM * sizeof(unsigned long long)));
-        CK(cudaMalloc((void **)&ctx->d_isrun, 640));
-        CK(cudaMalloc((void **)&ctx->d_runinfo, 2 * sizeof(long long)));
-    }
-    if (!ctx->hist_valid) {
-        CK(cudaMemsetAsync(ctx->d_hist, 0, NSYM * sizeof(unsigned long long), st));
-        symbol_hist_kernel<<<std::min<unsigned>(blocks_for((size_t)ctx->n_cols, 256), 4u * ctx->prop.multiProcessorCount), 256, 0, st>>>(
-            ctx->d_sym, ctx->n_cols, ctx->d_hist);
-        ctx->launches += 1;
-        ctx->hist_valid = true;
-    }
-    if (!ctx->runs_valid) {
-        const int KP = ctx->KP;
-        CK(ensure(ctx->d_P, ctx->cap_P, (size_t)ctx->n_sets * RUN_POWERS * KP * KP));
-        CK(ensure(ctx->d_sP, ctx->cap_sP, (size_t)ctx->n_sets * RUN_POWERS));
-        CK(ensure(ctx->d_ebar, ctx->cap_ebar, (size_t)ctx->n_sets * KP));
-        symbol_class_kernel<<<1, 640, 0, st>>>(ctx->d_Et, ctx->K, KP, ctx->n_sets, 1e-12, ctx->d_rep);
-        pick_run_class_kernel<<<1, 640, 0, st>>>(ctx->d_hist, ctx->d_rep, ctx->d_isrun, ctx->d_runinfo);
-        run_power_kernel<<<ctx->n_sets, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, ctx->d_P, ctx->d_sP, ctx->d_ebar);
-        ctx->launches += 3;
-        CK(cudaGetLastError());
-        ctx->runs_valid = true;
-    }
-    if (!ctx->use_runs_known) {
-        long long info[2] = {0, 0};
-        CK(cudaMemcpyAsync(info, ctx->d_runinfo, sizeof info, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->use_runs = info[1] * 2 > ctx->n_cols;      // a class holding most columns
-        ctx->use_runs_known = true;
-    }
+    if (ctx->runs_valid) return ITR_OK;
+    const int KP = ctx->KP;
+    CK(ensure(ctx->d_P, ctx->cap_P, (size_t)ctx->n_sets * RUN_POWERS * KP * KP));
+    CK(ensure(ctx->d_sP, ctx->cap_sP, (size_t)ctx->n_sets * RUN_POWERS));
+    CK(ensure(ctx->d_ebar, ctx->cap_ebar, (size_t)ctx->n_sets * KP));
+    symbol_class_kernel<<<1, 640, 0, st>>>(ctx->d_Et, ctx->K, KP, ctx->n_sets, 1e-12, ctx->d_rep);
+    pick_run_class_kernel<<<1, 640, 0, st>>>(ctx->d_hist, ctx->d_rep, ctx->d_isrun, ctx->d_runinfo);
+    run_power_kernel<<<ctx->n_sets, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, ctx->d_P, ctx->d_sP, ctx->d_ebar);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    ctx->runs_valid = true;
     return ITR_OK;
 }
 
@@ -762,11 +757,10 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
         ctx->cap_hll = n;
     }
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
-    bool runs = ctx->K <= 32 && !getenv("ITR_NO_RUNS");     // (the variable is for experiments and tests)
+    const bool runs = ctx->K <= 32 && ctx->use_runs && !getenv("ITR_NO_RUNS");   // (variable: experiments, tests)
     if (runs) {
         rc = prepare_runs(ctx, st);
         if (rc) return rc;
-        runs = ctx->use_runs;
     }
     phase_begin(ctx, ITR_PH_LOGLIK, st);
     if (runs) launch_forward_runs(ctx, ctx->d_ll, st);
