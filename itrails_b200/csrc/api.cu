@@ -69,8 +69,12 @@ struct itr_ctx {
     unsigned long long *d_hist = nullptr;
     uint8_t *d_isrun = nullptr;
     long long *d_runinfo = nullptr;
-    double *d_P = nullptr, *d_ebar = nullptr;
-    size_t cap_P = 0, cap_sP = 0, cap_ebar = 0;
+    double *d_P = nullptr, *d_Pb = nullptr, *d_ebar = nullptr, *d_ck_a = nullptr, *d_ck_b = nullptr;
+    size_t cap_P = 0, cap_Pb = 0, cap_sP = 0, cap_ebar = 0, cap_ck_a = 0, cap_ck_b = 0;
+    int64_t *d_tile_off = nullptr;
+    int32_t *d_tile_blk = nullptr;
+    size_t cap_tile_off = 0, cap_tile_blk = 0;
+    int64_t n_tiles = 0;
     bool runs_valid = false, use_runs = false;
 
     // log-likelihood
@@ -229,7 +233,8 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
                     ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
                     ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
-                    ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar};
+                    ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar, ctx->d_Pb, ctx->d_ck_a, ctx->d_ck_b,
+                    ctx->d_tile_off, ctx->d_tile_blk};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -275,6 +280,7 @@ extern "C" int64_t itr_num_blocks(const itr_ctx *ctx) { return ctx ? ctx->n_bloc
 // ---------------------------------------------------------------------------------
 // Data or model are about to change: drain every recursion stream first.
 static int quiesce(itr_ctx *ctx);
+static int prepare_runs(itr_ctx *ctx, cudaStream_t st);
 
 static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off, int64_t n_blocks) {
     CK(cudaSetDevice(ctx->device));
@@ -293,6 +299,12 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
         max_T = std::max(max_T, T);
         chunk_off[b + 1] = chunk_off[b] + (T + VCHUNK - 1) / VCHUNK;
     }
+    std::vector<int64_t> tile_off(n_blocks + 1, 0);
+    for (int64_t b = 0; b < n_blocks; ++b) tile_off[b + 1] = tile_off[b] + (off[b + 1] - off[b] + PTILE - 1) / PTILE;
+    const int64_t n_tiles = tile_off[n_blocks];
+    std::vector<int32_t> tile_blk(n_tiles);
+    for (int64_t b = 0; b < n_blocks; ++b)
+        std::fill(tile_blk.begin() + tile_off[b], tile_blk.begin() + tile_off[b + 1], (int32_t)b);
     const int64_t n_chunks = chunk_off[n_blocks];
     std::vector<int32_t> chunk_blk(n_chunks);
     for (int64_t b = 0; b < n_blocks; ++b)
@@ -307,6 +319,10 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(ensure(ctx->d_order, ctx->cap_order, (size_t)n_blocks));
     CK(ensure(ctx->d_chunk_off, ctx->cap_chunk_off, (size_t)(n_blocks + 1)));
     CK(ensure(ctx->d_chunk_blk, ctx->cap_chunk_blk, (size_t)std::max<int64_t>(n_chunks, 1)));
+    CK(ensure(ctx->d_tile_off, ctx->cap_tile_off, (size_t)(n_blocks + 1)));
+    CK(ensure(ctx->d_tile_blk, ctx->cap_tile_blk, (size_t)std::max<int64_t>(n_tiles, 1)));
+    CK(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tile_blk, tile_blk.data(), (size_t)n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_sym + n_cols, 0, 64 * sizeof(uint16_t), ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_sym, sym, (size_t)n_cols * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -332,8 +348,17 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     std::partial_sort(hist.begin(), hist.begin() + 4, hist.end(), std::greater<unsigned long long>());
     ctx->use_runs = 2 * (hist[0] + hist[1] + hist[2] + hist[3]) > (unsigned long long)n_cols;
     ctx->runs_valid = false;
+    ctx->n_tiles = n_tiles;
     ctx->h_off.assign(off, off + n_blocks + 1);
     ctx->h_order = order;
+    ctx->n_blocks = n_blocks;
+    ctx->n_cols = n_cols;
+    if (ctx->K > 0 && ctx->K <= 32 && ctx->use_runs) {
+        int prc = prepare_runs(ctx, ctx->stream);
+        if (prc) return prc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    }
     ctx->n_blocks = n_blocks;
     ctx->n_cols = n_cols;
     ctx->n_chunks = n_chunks;
@@ -410,12 +435,16 @@ int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, con
     phase_end(ctx, ITR_PH_EMIT_TABLE);
     ctx->launches += 3;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     ctx->n_sets = n_sets;
     ctx->K = K;
     ctx->KP = KP;
     ctx->have_path = ctx->have_post = false;
     ctx->runs_valid = false;
+    if (ctx->n_blocks > 0 && K <= 32 && ctx->use_runs) {
+        int prc = prepare_runs(ctx, ctx->stream);
+        if (prc) return prc;
+    }
+    CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     return ITR_OK;
 }
 
@@ -659,8 +688,11 @@ static int prepare_runs(itr_ctx *ctx, cudaStream_t st) {
     CK(ensure(ctx->d_ebar, ctx->cap_ebar, (size_t)ctx->n_sets * KP));
     symbol_class_kernel<<<1, 640, 0, st>>>(ctx->d_Et, ctx->K, KP, ctx->n_sets, 1e-12, ctx->d_rep);
     pick_run_class_kernel<<<1, 640, 0, st>>>(ctx->d_hist, ctx->d_rep, ctx->d_isrun, ctx->d_runinfo);
-    run_power_kernel<<<ctx->n_sets, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, ctx->d_P, ctx->d_sP, ctx->d_ebar);
-    ctx->launches += 3;
+    run_power_kernel<<<ctx->n_sets, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, 0, ctx->d_P, ctx->d_sP, ctx->d_ebar);
+    // backward powers (diag(e) a)^(2^k) for parameter set 0 (the posterior decodes set 0)
+    CK(ensure(ctx->d_Pb, ctx->cap_Pb, (size_t)RUN_POWERS * KP * KP));
+    run_power_kernel<<<1, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, 1, ctx->d_Pb, nullptr, nullptr);
+    ctx->launches += 4;
     CK(cudaGetLastError());
     ctx->runs_valid = true;
     return ITR_OK;
@@ -757,11 +789,7 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
         ctx->cap_hll = n;
     }
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
-    const bool runs = ctx->K <= 32 && ctx->use_runs && !getenv("ITR_NO_RUNS");   // (variable: experiments, tests)
-    if (runs) {
-        rc = prepare_runs(ctx, st);
-        if (rc) return rc;
-    }
+    const bool runs = ctx->K <= 32 && ctx->use_runs && ctx->runs_valid && !getenv("ITR_NO_RUNS");   // (variable: experiments, tests)
     phase_begin(ctx, ITR_PH_LOGLIK, st);
     if (runs) launch_forward_runs(ctx, ctx->d_ll, st);
     else launch_forward<0>(ctx, ctx->n_sets, ctx->d_ll, nullptr, st, 0);
@@ -867,10 +895,64 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
     const size_t n = (size_t)ctx->n_cols * ctx->K;
     CK(cudaStreamSynchronize(st));
     CK(ensure(ctx->d_post, ctx->cap_post, n));
-    CK(ensure(ctx->d_beta, ctx->cap_beta, n));
+    if (!(ctx->K <= 32 && ctx->use_runs && ctx->runs_valid && !getenv("ITR_NO_RUNS"))) CK(ensure(ctx->d_beta, ctx->cap_beta, n));
     // forward (alpha -> d_post) on the posterior stream, backward (beta -> d_beta) on
     // the second stream, concurrently; then the combine on the posterior stream.
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    if (ctx->K <= 32 && ctx->use_runs && ctx->runs_valid && !getenv("ITR_NO_RUNS")) {
+        // two-pass posterior: checkpoint sweeps (forward || backward), then one warp per tile
+        const int K = ctx->K, KP = ctx->KP;
+        CK(ensure(ctx->d_ck_a, ctx->cap_ck_a, (size_t)(ctx->n_tiles + 1) * KP));
+        CK(ensure(ctx->d_ck_b, ctx->cap_ck_b, (size_t)(ctx->n_tiles + 1) * KP));
+        phase_begin(ctx, ITR_PH_POST_TOTAL, st);
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        const Geometry g = geometry(ctx, ctx->n_blocks, 12);
+        const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+        const ChainSet csb = chain_set(ctx, 1, 1), csf = chain_set(ctx, 1, 3);
+        cudaMemsetAsync(csb.queue, 0, sizeof(unsigned int), ctx->stream2);
+        cudaMemsetAsync(csf.queue, 0, sizeof(unsigned int), st);
+        const int wt = 4;
+        const size_t sht = (size_t)wt * (2 * KP + PTILE * (KP + 1) + PTILE) * sizeof(double);
+        const unsigned gt = (unsigned)std::min<int64_t>((ctx->n_tiles + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6);
+#define POST2(KT)                                                                                                     \
+    do {                                                                                                              \
+        phase_begin(ctx, ITR_PH_POST_BWD, ctx->stream2);                                                              \
+        checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, ctx->stream2>>>(                                   \
+            csb, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
+        phase_end(ctx, ITR_PH_POST_BWD, ctx->stream2);                                                                \
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));                                                              \
+        phase_begin(ctx, ITR_PH_POST_FWD, st);                                                                        \
+        checkpoint_sweep_kernel<KT, 0><<<g.grid, g.warps * 32, sh, st>>>(                                             \
+            csf, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_a);  \
+        phase_end(ctx, ITR_PH_POST_FWD, st);                                                                          \
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));                                                                 \
+        CK(cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht));  \
+        phase_begin(ctx, ITR_PH_POST_COMBINE, st);                                                                    \
+        posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
+                                                             ctx->n_tiles, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, \
+                                                             ctx->d_ck_b, K, ctx->d_post);                            \
+        phase_end(ctx, ITR_PH_POST_COMBINE, st);                                                                      \
+    } while (0)
+        switch ((K + 3) / 4) {
+            case 1: POST2(4); break;
+            case 2: POST2(8); break;
+            case 3: POST2(12); break;
+            case 4: POST2(16); break;
+            case 5: POST2(20); break;
+            case 6: POST2(24); break;
+            case 7: POST2(28); break;
+            default: POST2(32); break;
+        }
+#undef POST2
+        phase_end(ctx, ITR_PH_POST_TOTAL, st);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        ctx->have_post = true;
+        if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (!ctx->async) CK(cudaStreamSynchronize(st));
+        return ITR_OK;
+    }
     const int n_groups = (post && ctx->n_blocks >= 16 && !getenv("ITR_POST_ONE_GROUP")) ? 8 : 1;
     if (n_groups > 1) {
         // Blocks are independent: run them in groups of similar length (contiguous ranges

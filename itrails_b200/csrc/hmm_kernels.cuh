@@ -421,14 +421,15 @@ pick_run_class_kernel(const unsigned long long *__restrict__ hist, const int32_t
 // One CTA (32 x 32 threads) per parameter set.
 __global__ void __launch_bounds__(1024)
 run_power_kernel(const double *__restrict__ A, const double *__restrict__ Et, const long long *__restrict__ info,
-                 int KP, double *__restrict__ P, int32_t *__restrict__ sP, double *__restrict__ ebar) {
+                 int KP, int left, double *__restrict__ P, int32_t *__restrict__ sP, double *__restrict__ ebar) {
     __shared__ double M[32][33], N[32][33];
     __shared__ unsigned int hi_max;
     const int set = blockIdx.x, i = threadIdx.y, j = threadIdx.x;
     const int r = (int)info[0];
-    const double e = Et[((size_t)set * NSYM + r) * KP + j];
+    // left = 0: a diag(e) (forward runs); left = 1: diag(e) a (backward runs, reference orientation)
+    const double e = Et[((size_t)set * NSYM + r) * KP + (left ? i : j)];
     M[i][j] = A[((size_t)set * KP + i) * KP + j] * e;
-    if (i == 0) ebar[(size_t)set * KP + j] = e;
+    if (i == 0 && ebar) ebar[(size_t)set * KP + j] = Et[((size_t)set * NSYM + r) * KP + j];
     int shift = 0;
     __syncthreads();
     for (int sq = 0; sq < RUN_POWERS; ++sq) {  // M <- M M: M^2, M^4, ..., M^32
@@ -451,7 +452,7 @@ run_power_kernel(const double *__restrict__ A, const double *__restrict__ Et, co
         __syncthreads();
         M[i][j] = N[i][j];
         P[(((size_t)set * RUN_POWERS + sq) * KP + i) * KP + j] = N[i][j];
-        if (i == 0 && j == 0) sP[set * RUN_POWERS + sq] = shift;
+        if (i == 0 && j == 0 && sP) sP[set * RUN_POWERS + sq] = shift;
         __syncthreads();
     }
 }
@@ -543,6 +544,227 @@ forward_runs_kernel(ChainSet cs, const double *__restrict__ A, const double *__r
         double tot = warp_sum(x[0]);
         if (lane == 0 && loglik)
             loglik[(size_t)set * cs.n_blocks + blk] = log(tot) + (double)shift * 0.6931471805599453094;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Two-pass posterior (K <= 32, alignments with a dominant emission class).
+//
+// Pass 1 (latency bound, but short): run-compressed forward and backward sweeps, one warp
+// per block, that only store *checkpoints* — the forward vector entering every 32-column
+// tile and the backward vector at every tile's last column.  Power steps are confined to
+// a tile so that every checkpoint is landed on exactly.
+// Pass 2 (throughput bound): one warp per tile recomputes the 32 forward vectors of its
+// tile from the checkpoint into shared memory, walks the tile backwards from the backward
+// checkpoint forming alpha*beta, normalises per column and writes the posterior rows
+// with coalesced stores.  HBM traffic is the posterior matrix itself (8K bytes/column)
+// plus 2 x 8 bytes/column of checkpoints, instead of alpha + beta + three passes.
+// Backward orientation is the reference's: beta_t = (beta_{t+1} * e(V_{t+1})) @ a
+// (optimizer.py:210); in a run that is beta_{t+n} (diag(e) a)^n.
+// ---------------------------------------------------------------------------------
+constexpr int PTILE = 32;
+
+// DIR 0: forward checkpoints ck[tile] = alpha_{32 m - 1} (state entering tile m; tile 0 unused)
+// DIR 1: backward checkpoints ck[tile] = beta_{32 m + 31} (last tile of a block: not stored, it is 1)
+template <int KT, int DIR>
+__global__ void __launch_bounds__(256)
+checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ PI,
+                        const double *__restrict__ Et, const double *__restrict__ P, const double *__restrict__ ebar,
+                        const uint8_t *__restrict__ isrun, const int64_t *__restrict__ tile_off, int K,
+                        double *__restrict__ ck) {
+    constexpr int KP = 32;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xs = smem + (size_t)warp * 2 * KP;
+    const int n_chains = cs.n_blocks;
+    const double *etl = Et + lane;
+    Cols<KT, 1, true> acol;
+    acol.load(A, KP, lane);
+    const double eb = __ldg(ebar + lane);
+
+    for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
+        const int blk = cs.order[c];
+        const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
+        const SymTile st{cs.sym + beg, T};
+        double *ckb = ck + (size_t)tile_off[blk] * KP + lane;
+        const int64_t n_tiles = (T + PTILE - 1) / PTILE;
+        auto run_mask = [&](unsigned v, int64_t t0) {
+            return __ballot_sync(FULL, (t0 + lane >= 0) && (t0 + lane < T) && __ldg(isrun + v));
+        };
+        double x[1];
+        int buf = 0, steps = 0;
+        // one step of n columns with power k (n = 2 << k), or a single column
+        auto power_step = [&](int k) {
+            Cols<KT, 1, true> pcol;
+            pcol.load(P + (size_t)k * KP * KP, KP, lane);
+            double *xb = xs + buf * KP;
+            buf ^= 1;
+            xb[lane] = x[0];
+            __syncwarp();
+            double y[1];
+            matvec<KT, 1, true>(xb, pcol, KT, y);
+            x[0] = y[0];
+            if ((++steps & 3) == 0) (void)rescale_pow2<1>(x);
+        };
+        if (DIR == 0) {
+            unsigned vcur = st.load(0, lane), vnxt = st.load(PTILE, lane);
+            unsigned mcur = run_mask(vcur, 0);
+            x[0] = __ldg(PI + lane) * __ldg(etl + __shfl_sync(FULL, vcur, 0) * KP);
+            int pos = 1;
+            for (int64_t m = 0; m < n_tiles; ++m) {
+                const int64_t t0 = m * PTILE;
+                if (m > 0) ckb[(size_t)m * KP] = x[0];
+                const int end = (int)min((int64_t)PTILE, T - t0);
+                while (pos < end) {
+                    const unsigned rest = mcur >> pos;
+                    const int nrun = (rest == 0xffffffffu) ? 32 : __ffs(~rest) - 1;
+                    if (nrun >= 2) {
+                        const int k = min(31 - __clz(nrun), RUN_POWERS) - 1;
+                        power_step(k);
+                        pos += 2 << k;
+                    } else {
+                        const double e = nrun ? eb : __ldg(etl + __shfl_sync(FULL, vcur, pos) * KP);
+                        double *xb = xs + buf * KP;
+                        buf ^= 1;
+                        xb[lane] = x[0];
+                        __syncwarp();
+                        double y[1];
+                        matvec<KT, 1, true>(xb, acol, KT, y);
+                        x[0] = y[0] * e;
+                        if ((++steps & 3) == 0) (void)rescale_pow2<1>(x);
+                        pos += 1;
+                    }
+                }
+                pos = 0;
+                vcur = vnxt;
+                mcur = run_mask(vcur, t0 + PTILE);
+                vnxt = st.load(t0 + 2 * PTILE, lane);
+            }
+        } else {
+            // walk tiles from the last to the first; inside a tile from high columns to low.
+            // State: beta at column t_cur.  A step down by n consumes the emissions of columns
+            // t_cur, t_cur - 1, ..., t_cur - n + 1.
+            int64_t m = n_tiles - 1;
+            unsigned vcur = st.load(m * PTILE, lane), vnxt = st.load((m - 1) * PTILE, lane);
+            unsigned mcur = run_mask(vcur, m * PTILE);
+            x[0] = (lane < K) ? 1.0 : 0.0;
+            int pos = (int)(T - 1 - m * PTILE);              // position of t_cur inside the tile
+            for (; m >= 0; --m) {
+                if (m < n_tiles - 1) ckb[(size_t)m * KP] = x[0];       // beta_{32 m + 31}
+                // columns of this tile still to consume: pos, pos-1, ..., 0  (column 0 of the block
+                // is never consumed: beta_0 needs e(V_1) only)
+                const int lowest = (m == 0) ? 1 : 0;
+                while (pos >= lowest) {
+                    const unsigned up = mcur << (31 - pos);                  // bit 31 = column `pos`
+                    int nrun = (up == 0xffffffffu) ? 32 : __clz(~up);         // run columns pos, pos-1, ...
+                    nrun = min(nrun, pos - lowest + 1);
+                    if (nrun >= 2) {
+                        const int k = min(31 - __clz(nrun), RUN_POWERS) - 1;
+                        power_step(k);
+                        pos -= 2 << k;
+                    } else {
+                        const double e = nrun ? eb : __ldg(etl + __shfl_sync(FULL, vcur, pos) * KP);
+                        double *xb = xs + buf * KP;
+                        buf ^= 1;
+                        xb[lane] = x[0] * e;
+                        __syncwarp();
+                        double y[1];
+                        matvec<KT, 1, true>(xb, acol, KT, y);
+                        x[0] = y[0];
+                        if ((++steps & 3) == 0) (void)rescale_pow2<1>(x);
+                        pos -= 1;
+                    }
+                }
+                pos = PTILE - 1;
+                vcur = vnxt;
+                mcur = run_mask(vcur, (m - 1) * PTILE);
+                vnxt = st.load((m - 2) * PTILE, lane);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Pass 2: one warp per tile.  al: forward vectors of the tile, stride KP + 1.
+template <int KT>
+__global__ void __launch_bounds__(256)
+posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
+                       const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
+                       int64_t n_tiles_total, const double *__restrict__ A, const double *__restrict__ PI,
+                       const double *__restrict__ Et, const double *__restrict__ ck_a,
+                       const double *__restrict__ ck_b, int K, double *__restrict__ post) {
+    constexpr int KP = 32, LD = KP + 1;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double *xs = smem + (size_t)warp * (2 * KP + PTILE * LD + PTILE);
+    double *al = xs + 2 * KP;
+    double *rcp = al + PTILE * LD;
+    const double *etl = Et + lane;
+    Cols<KT, 1, true> acol;
+    acol.load(A, KP, lane);
+
+    for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < n_tiles_total; g += (int64_t)gridDim.x * nwarps) {
+        const int blk = tile_blk[g];
+        const int64_t m = g - tile_off[blk];
+        const int64_t beg = off[blk], T = off[blk + 1] - beg;
+        const int64_t t0 = m * PTILE;
+        const int n = (int)min((int64_t)PTILE, T - t0);
+        const unsigned v = (lane < n) ? (unsigned)__ldg(sym + beg + t0 + lane) : 0u;
+        int buf = 0;
+        // ---- forward through the tile
+        double x[1];
+        int first = 0;
+        if (m == 0) {
+            x[0] = __ldg(PI + lane) * __ldg(etl + __shfl_sync(FULL, v, 0) * KP);
+            al[lane] = x[0];
+            first = 1;
+        } else {
+            x[0] = __ldg(ck_a + (size_t)g * KP + lane);
+        }
+        double e_next = __ldg(etl + __shfl_sync(FULL, v, first) * KP);
+        for (int i = first; i < n; ++i) {
+            const double e = e_next;
+            e_next = __ldg(etl + __shfl_sync(FULL, v, (i + 1) & 31) * KP);
+            double *xb = xs + buf * KP;
+            buf ^= 1;
+            xb[lane] = x[0];
+            __syncwarp();
+            double y[1];
+            matvec<KT, 1, true>(xb, acol, KT, y);
+            x[0] = y[0] * e;
+            if ((i & 7) == 7) (void)rescale_pow2<1>(x);
+            al[i * LD + lane] = x[0];
+        }
+        // ---- backward through the tile, forming alpha * beta in place
+        double b[1];
+        b[0] = (t0 + n == T) ? ((lane < K) ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + lane);
+        for (int i = n - 1; i >= 0; --i) {
+            al[i * LD + lane] *= b[0];
+            if (i == 0) break;
+            const double e = __ldg(etl + __shfl_sync(FULL, v, i) * KP);
+            double *xb = xs + buf * KP;
+            buf ^= 1;
+            xb[lane] = b[0] * e;
+            __syncwarp();
+            double y[1];
+            matvec<KT, 1, true>(xb, acol, KT, y);
+            b[0] = y[0];
+            if ((i & 7) == 0) (void)rescale_pow2<1>(b);
+        }
+        __syncwarp();
+        // ---- normalise per column (lane = column) and write rows with coalesced stores
+        if (lane < n) {
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) s += al[lane * LD + k];
+            rcp[lane] = 1.0 / s;
+        }
+        __syncwarp();
+        double *out = post + (size_t)(beg + t0) * K;
+        for (int e = lane; e < n * K; e += 32) {
+            const int col = e / K, k = e - col * K;
+            out[e] = al[col * LD + k] * rcp[col];
+        }
         __syncwarp();
     }
 }
