@@ -294,15 +294,18 @@ def main():
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, args.steps)
+        e2e_ms = []
         for _ in range(n_e2e):
+            t1 = time.perf_counter()
             step_e2e()
-        step_e2e()
+            e2e_ms.append((time.perf_counter() - t1) * 1e3)
         barrier()
         dte = D.allreduce_max((time.perf_counter() - t0) / n_e2e)
         h2d = sym.nbytes + off.nbytes + (a.nbytes + b.nbytes + pi.nbytes) + log_a.nbytes + log_E.nbytes + omega0.nbytes
         d2h = ncol * 1 + ncol * K * 8 + 8 * len(V_lst)
         e2e = {"value": total_cols / dte, "unit": "columns/s", "ms_per_step": dte * 1e3,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "per_step_ms": [round(x, 2) for x in e2e_ms]}
         eng.load_packed(sym, off)
         eng.set_model(a, b, pi)
 

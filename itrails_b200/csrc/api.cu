@@ -54,6 +54,7 @@ struct itr_ctx {
     size_t cap_sym = 0, cap_off = 0, cap_order = 0, cap_chunk_off = 0, cap_chunk_blk = 0;
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_order;
+    std::vector<int64_t> h_tile_off;
     std::vector<cudaStream_t> grp_streams;     // 2 per posterior group
     std::vector<cudaEvent_t> grp_events;       // 2 per posterior group
 
@@ -349,6 +350,7 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     ctx->use_runs = 2 * (hist[0] + hist[1] + hist[2] + hist[3]) > (unsigned long long)n_cols;
     ctx->runs_valid = false;
     ctx->n_tiles = n_tiles;
+    ctx->h_tile_off = tile_off;
     ctx->h_off.assign(off, off + n_blocks + 1);
     ctx->h_order = order;
     ctx->n_blocks = n_blocks;
@@ -914,7 +916,26 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         cudaMemsetAsync(csf.queue, 0, sizeof(unsigned int), st);
         const int wt = 4;
         const size_t sht = (size_t)wt * (2 * KP + PTILE * (KP + 1) + PTILE) * sizeof(double);
-        const unsigned gt = (unsigned)std::min<int64_t>((ctx->n_tiles + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6);
+        // Pass 2 runs in slices of consecutive tiles (= consecutive columns); with a host
+        // destination every slice is downloaded on a copy stream while the next one computes.
+        const int n_slices = post ? (int)std::min<int64_t>(std::min<int64_t>(8, ctx->n_blocks), std::max<int64_t>(1, ctx->n_tiles / 4096)) : 1;
+        if (post && ctx->grp_streams.empty()) {
+            cudaStream_t s2 = nullptr;
+            cudaEvent_t e2 = nullptr;
+            CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            ctx->grp_streams.push_back(s2);
+            CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            ctx->grp_events.push_back(e2);
+        }
+        std::vector<int64_t> slice_tile(n_slices + 1), slice_col(n_slices + 1);
+        for (int q = 0; q <= n_slices; ++q) {
+            // slice boundaries on block boundaries keep the tile <-> column mapping trivial
+            const int64_t b = ctx->n_blocks * q / n_slices;
+            slice_col[q] = ctx->h_off[b];
+            slice_tile[q] = ctx->h_tile_off[b];
+        }
+        cudaStream_t scopy = post ? ctx->grp_streams[0] : nullptr;
+        cudaEvent_t ecopy = post ? ctx->grp_events[0] : nullptr;
 #define POST2(KT)                                                                                                     \
     do {                                                                                                              \
         phase_begin(ctx, ITR_PH_POST_BWD, ctx->stream2);                                                              \
@@ -929,9 +950,21 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));                                                                 \
         CK(cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht));  \
         phase_begin(ctx, ITR_PH_POST_COMBINE, st);                                                                    \
-        posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
-                                                             ctx->n_tiles, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, \
-                                                             ctx->d_ck_b, K, ctx->d_post);                            \
+        for (int q = 0; q < n_slices; ++q) {                                                                          \
+            const int64_t nt = slice_tile[q + 1] - slice_tile[q];                                                     \
+            if (nt <= 0) continue;                                                                                    \
+            const unsigned gt = (unsigned)std::min<int64_t>((nt + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6); \
+            posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
+                                                                 slice_tile[q], slice_tile[q + 1], ctx->d_A, ctx->d_PI, \
+                                                                 ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K, ctx->d_post); \
+            ctx->launches += 1;                                                                                       \
+            if (post) {                                                                                               \
+                CK(cudaEventRecord(ecopy, st));                                                                       \
+                CK(cudaStreamWaitEvent(scopy, ecopy, 0));                                                             \
+                const size_t o = (size_t)slice_col[q] * K, len = (size_t)(slice_col[q + 1] - slice_col[q]) * K;       \
+                CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, scopy));  \
+            }                                                                                                         \
+        }                                                                                                             \
         phase_end(ctx, ITR_PH_POST_COMBINE, st);                                                                      \
     } while (0)
         switch ((K + 3) / 4) {
@@ -946,10 +979,13 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         }
 #undef POST2
         phase_end(ctx, ITR_PH_POST_TOTAL, st);
-        ctx->launches += 3;
+        ctx->launches += 2;
         CK(cudaGetLastError());
         ctx->have_post = true;
-        if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (post) {                       // the posterior stream also waits for the downloads
+            CK(cudaEventRecord(ecopy, scopy));
+            CK(cudaStreamWaitEvent(st, ecopy, 0));
+        }
         if (!ctx->async) CK(cudaStreamSynchronize(st));
         return ITR_OK;
     }

@@ -691,7 +691,7 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
                        const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
-                       int64_t n_tiles_total, const double *__restrict__ A, const double *__restrict__ PI,
+                       int64_t g_begin, int64_t g_end, const double *__restrict__ A, const double *__restrict__ PI,
                        const double *__restrict__ Et, const double *__restrict__ ck_a,
                        const double *__restrict__ ck_b, int K, double *__restrict__ post) {
     constexpr int KP = 32, LD = KP + 1;
@@ -704,7 +704,7 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
     Cols<KT, 1, true> acol;
     acol.load(A, KP, lane);
 
-    for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < n_tiles_total; g += (int64_t)gridDim.x * nwarps) {
+    for (int64_t g = g_begin + (int64_t)blockIdx.x * nwarps + warp; g < g_end; g += (int64_t)gridDim.x * nwarps) {
         const int blk = tile_blk[g];
         const int64_t m = g - tile_off[blk];
         const int64_t beg = off[blk], T = off[blk + 1] - beg;
