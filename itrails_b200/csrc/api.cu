@@ -589,9 +589,16 @@ static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alp
         cs.order += first;
         cs.n_blocks = count;
     }
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    if (K > 32 && K <= 96) {        // one CTA of ceil(K/32) warps per chain, columns of a in registers
+        const int grid = (int)std::min<int64_t>((int64_t)n_sets * cs.n_blocks, (int64_t)ctx->prop.multiProcessorCount * 8);
+        if (K <= 64) sweep_mw_kernel<2, 0, MODE><<<grid, 64, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha);
+        else sweep_mw_kernel<3, 0, MODE><<<grid, 96, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha);
+        ctx->launches += 1;
+        return;
+    }
     const Geometry g = geometry(ctx, (int64_t)n_sets * cs.n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
 #define FWD_REG(KT) \
     forward_kernel<KT, 1, true, MODE><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha)
 #define FWD_GEN(NS) \
@@ -609,9 +616,16 @@ static void launch_backward(itr_ctx *ctx, cudaStream_t st, int slot = 1, int fir
         cs.order += first;
         cs.n_blocks = count;
     }
+    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    if (K > 32 && K <= 96) {
+        const int grid = (int)std::min<int64_t>(cs.n_blocks, (int64_t)ctx->prop.multiProcessorCount * 8);
+        if (K <= 64) sweep_mw_kernel<2, 1, 1><<<grid, 64, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, nullptr, ctx->d_beta);
+        else sweep_mw_kernel<3, 1, 1><<<grid, 96, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, nullptr, ctx->d_beta);
+        ctx->launches += 1;
+        return;
+    }
     const Geometry g = geometry(ctx, cs.n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
 #define BWD_REG(KT) backward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_Et, K, ctx->d_beta)
 #define BWD_GEN(NS) backward_kernel<4, NS, false><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_Et, K, ctx->d_beta)
     ITR_DISPATCH_K(K, BWD_REG, BWD_GEN);

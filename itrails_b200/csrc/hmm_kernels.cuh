@@ -855,6 +855,132 @@ backward_kernel(ChainSet cs, const double *__restrict__ A, const double *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Plain sweeps for 32 < K <= 32 NW (NW = 2, 3): one CTA of NW warps per chain, warp w
+// owns states [32 w, 32 w + 32) and keeps their columns of `a` in registers (64 NW
+// registers per lane).  Per column: every warp publishes its 32 values, one bar.sync,
+// every lane reads all 32 NW values with broadcast LDS.128 and runs its dot product.
+// The power-of-two rescaling uses the maximum exponent over all warps, exchanged with
+// the values.  DIR 0: forward (MODE 0 log-likelihood, MODE 1 also stores alpha);
+// DIR 1: backward in the reference's orientation (stores beta).
+// ---------------------------------------------------------------------------------
+template <int NW, int DIR, int MODE>
+__global__ void __launch_bounds__(32 * NW)
+sweep_mw_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ PI,
+                const double *__restrict__ Et, int K, double *__restrict__ loglik, double *__restrict__ out) {
+    constexpr int KP = 32 * NW;
+    __shared__ __align__(16) double xs[2][KP];
+    __shared__ unsigned hi_s[2][NW];
+    __shared__ int chain_s;
+    __shared__ double tot_s[NW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = 32 * warp + lane;                       // owned state
+    const int n_chains = cs.n_sets * cs.n_blocks;
+
+    for (;;) {
+        if (threadIdx.x == 0) chain_s = (int)atomicAdd(cs.queue, 1u);
+        __syncthreads();
+        const int c = chain_s;
+        __syncthreads();
+        if (c >= n_chains) break;
+        const int set = c / cs.n_blocks;
+        const int blk = cs.order[c % cs.n_blocks];
+        const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
+        const uint16_t *symp = cs.sym + beg;
+        const double *etj = Et + (size_t)set * NSYM * KP + j;
+        double col[KP];                                   // column j of a
+#pragma unroll
+        for (int i = 0; i < KP; ++i) col[i] = __ldg(A + ((size_t)set * KP + i) * KP + j);
+
+        double x;
+        long long shift = 0;
+        int buf = 0;
+        // x_new[j] = sum_i xs[i] * a[i][j]
+        auto dot = [&](const double *xv) {
+            const double2 *x2 = reinterpret_cast<const double2 *>(xv);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < KP; i += 4) {
+                const double2 p = x2[i / 2], q = x2[i / 2 + 1];
+                a0 = fma(p.x, col[i], a0);
+                a1 = fma(p.y, col[i + 1], a1);
+                a2 = fma(q.x, col[i + 2], a2);
+                a3 = fma(q.y, col[i + 3], a3);
+            }
+            return (a0 + a1) + (a2 + a3);
+        };
+        // publish `v` (and, every 8th column, this warp's maximum exponent); returns the common
+        // power-of-two scale to apply to the *next* vector (1.0 when no rescale is due)
+        auto exchange = [&](double v, bool with_max) {
+            xs[buf][j] = v;
+            if (with_max) {
+                const unsigned hi = __reduce_max_sync(FULL, (unsigned)__double2hiint(v));
+                if (lane == 0) hi_s[buf][warp] = hi;
+            }
+            __syncthreads();
+        };
+        auto common_scale = [&](int *removed) {
+            unsigned hi = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) hi = max(hi, hi_s[buf][w]);
+            const int ex = (int)(hi >> 20);
+            if (ex == 0 || ex == 0x7ff) { *removed = 0; return 1.0; }
+            *removed = ex - 1023;
+            return __hiloint2double((2046 - ex) << 20, 0);
+        };
+        if (DIR == 0) {
+            x = __ldg(PI + (size_t)set * KP + j) * __ldg(etj + (unsigned)__ldg(symp) * KP);
+            double *ao = (MODE == 1) ? out + (size_t)beg * K + j : nullptr;
+            if (MODE == 1 && j < K) ao[0] = x;
+            double e_next = __ldg(etj + (unsigned)__ldg(symp + 1) * KP);
+            for (int64_t t = 1; t < T; ++t) {
+                const double e = e_next;
+                e_next = __ldg(etj + (unsigned)__ldg(symp + t + 1) * KP);   // (64 columns of slack)
+                const bool resc = (t & 7) == 0;
+                exchange(x, resc);
+                double y = dot(xs[buf]);
+                if (resc) {
+                    int removed;
+                    y *= common_scale(&removed);          // scale of the previous vector, applied here
+                    shift += removed;
+                }
+                x = y * e;
+                buf ^= 1;
+                if (MODE == 1 && j < K) ao[(size_t)t * K] = x;
+            }
+            const double part = warp_sum(x);
+            if (lane == 0) tot_s[warp] = part;
+            __syncthreads();
+            if (threadIdx.x == 0 && loglik) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tot += tot_s[w];
+                loglik[(size_t)set * cs.n_blocks + blk] = log(tot) + (double)shift * 0.6931471805599453094;
+            }
+        } else {
+            double *bo = out + (size_t)beg * K + j;
+            x = (j < K) ? 1.0 : 0.0;
+            if (j < K) bo[(size_t)(T - 1) * K] = x;
+            double e_next = __ldg(etj + (unsigned)__ldg(symp + T - 1) * KP);
+            for (int64_t t = T - 2; t >= 0; --t) {
+                const double e = e_next;                  // emission of column t + 1
+                e_next = __ldg(etj + (unsigned)__ldg(symp + (t > 0 ? t : 0)) * KP);
+                const bool resc = (t & 7) == 0;
+                exchange(x * e, resc);
+                double y = dot(xs[buf]);
+                if (resc) {
+                    int removed;
+                    y *= common_scale(&removed);
+                }
+                x = y;
+                buf ^= 1;
+                if (j < K) bo[(size_t)t * K] = x;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // post[t][j] = alpha[t][j] * beta[t][j] / sum_j(alpha[t][j] * beta[t][j])
 // (optimizer.py:231-237; scales cancel).  `post` holds alpha on entry.  HBM-bound:
 // a CTA stages COLS columns through shared memory with coalesced loads and stores.
