@@ -133,7 +133,20 @@ def cpu_sample(V_lst, max_cols):
 
 
 # ---------------------------------------------------------------------------------
+def _emit(line):
+    """Print the one JSON line on the real stdout (see main: fd 1 is pointed at stderr while
+    the benchmark runs, because NCCL and other native libraries write banners to it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -182,7 +195,7 @@ def main():
             "breakdown": {k: ncol * args.steps / max(v, 1e-12) for k, v in zip(("forward", "viterbi", "posterior"), parts)},
             "e2e": {"value": val, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -371,7 +384,7 @@ def main():
         "cpu_baseline": cpu,
         "e2e": e2e,
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
