@@ -22,6 +22,8 @@ from .engine import Engine  # noqa: F401
 from .read_data import (get_idx_state, get_obs_state_dct, maf_parser,  # noqa: F401
                         parse_coordinates)
 from .cutpoints import cutpoints_AB, cutpoints_ABC, get_times  # noqa: F401
+# (the function `optimizer` is not re-exported: it would shadow the module of the same name,
+# which — as in the reference — is imported as `from itrails_b200.optimizer import optimizer`)
 from .optimizer import (loglik_wrapper, loglik_wrapper_par, post_prob_wrapper,  # noqa: F401
-                        viterbi_wrapper, optimizer, optimization_wrapper)
+                        viterbi_wrapper, optimization_wrapper)
 from .get_trans_emiss import trans_emiss_calc  # noqa: F401

@@ -496,6 +496,10 @@ forward_runs_kernel(ChainSet cs, const double *__restrict__ A, const double *__r
         int buf = 0, steps = 0;
         int pos = 1;                               // position of the next column inside the current tile
         for (int64_t t0 = 0; t0 < T; t0 += 32) {
+            // issued at the top of the tile so that their latency hides under the tile's steps:
+            // the run flags of tile + 2 (gathered by symbol) and the symbols of tile + 3
+            const bool fnn = (t0 + 64 + lane < T) && __ldg(isrun + vnn);
+            const unsigned vn3 = st.load(t0 + 96, lane);
             const unsigned long long win = (unsigned long long)mcur | ((unsigned long long)mnxt << 32);
             const int end = (int)min((int64_t)32, T - t0);
             while (pos < end) {
@@ -537,9 +541,9 @@ forward_runs_kernel(ChainSet cs, const double *__restrict__ A, const double *__r
             pos -= 32;
             vcur = vnxt;
             vnxt = vnn;
+            vnn = vn3;
             mcur = mnxt;
-            mnxt = run_mask(vnxt, t0 + 64);
-            vnn = st.load(t0 + 96, lane);
+            mnxt = __ballot_sync(FULL, fnn);
         }
         double tot = warp_sum(x[0]);
         if (lane == 0 && loglik)
@@ -615,6 +619,9 @@ checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double 
             for (int64_t m = 0; m < n_tiles; ++m) {
                 const int64_t t0 = m * PTILE;
                 if (m > 0) ckb[(size_t)m * KP] = x[0];
+                // next tile's run flags and the symbols of the tile after it: issued now, used at the tile's end
+                const bool fn = (t0 + PTILE + lane < T) && __ldg(isrun + vnxt);
+                const unsigned vn2 = st.load(t0 + 2 * PTILE, lane);
                 const int end = (int)min((int64_t)PTILE, T - t0);
                 while (pos < end) {
                     const unsigned rest = mcur >> pos;
@@ -638,8 +645,8 @@ checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double 
                 }
                 pos = 0;
                 vcur = vnxt;
-                mcur = run_mask(vcur, t0 + PTILE);
-                vnxt = st.load(t0 + 2 * PTILE, lane);
+                mcur = __ballot_sync(FULL, fn);
+                vnxt = vn2;
             }
         } else {
             // walk tiles from the last to the first; inside a tile from high columns to low.
@@ -652,6 +659,9 @@ checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double 
             int pos = (int)(T - 1 - m * PTILE);              // position of t_cur inside the tile
             for (; m >= 0; --m) {
                 if (m < n_tiles - 1) ckb[(size_t)m * KP] = x[0];       // beta_{32 m + 31}
+                const int64_t tn = (m - 1) * PTILE;                     // next (lower) tile
+                const bool fn = (tn + lane >= 0) && (tn + lane < T) && __ldg(isrun + vnxt);
+                const unsigned vn2 = st.load((m - 2) * PTILE, lane);
                 // columns of this tile still to consume: pos, pos-1, ..., 0  (column 0 of the block
                 // is never consumed: beta_0 needs e(V_1) only)
                 const int lowest = (m == 0) ? 1 : 0;
@@ -678,8 +688,8 @@ checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double 
                 }
                 pos = PTILE - 1;
                 vcur = vnxt;
-                mcur = run_mask(vcur, (m - 1) * PTILE);
-                vnxt = st.load((m - 2) * PTILE, lane);
+                mcur = __ballot_sync(FULL, fn);
+                vnxt = vn2;
             }
         }
         __syncwarp();

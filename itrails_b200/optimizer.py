@@ -159,17 +159,21 @@ def optimization_wrapper(arg_lst, optimized_params, case, d, V_lst, res_name, in
     """Objective (optimizer.py:396-583): parameters -> model build -> log-likelihood,
     appended to ``<prefix>.optimization_history.csv``; ``<prefix>.best_model.yaml`` is
     rewritten on improvement; returns ``-loglik``."""
-    from .get_trans_emiss import trans_emiss_calc
-
     output_dir, output_prefix = os.path.split(res_name)
     best_model_yaml = os.path.join(output_dir, f"{output_prefix}.best_model.yaml")
     d_copy = d.copy()
     for i, param in enumerate(optimized_params):
         d_copy[param] = arg_lst[i]
     derive_times(d_copy, case)
-    a, b, pi, _hidden, _observed = trans_emiss_calc(
-        *model_args(d_copy), d_copy["n_int_AB"], d_copy["n_int_ABC"], "standard", "standard")
-    loglik = loglik_wrapper(a, b, pi, V_lst)
+    # trans_emiss_calc + loglik_wrapper of the reference (optimizer.py:543-567), without the
+    # round trip of (a, b, pi) through the host: the builder leaves the model installed on
+    # the device next to this rank's resident blocks.
+    eng, _ = _resident(V_lst)
+    eng.build_model(np.array([model_args(d_copy)]), d_copy["n_int_AB"], d_copy["n_int_ABC"], fetch=False)
+    total = eng.loglik()
+    if dist_.is_active():
+        total = dist_.allreduce_sum(total, eng.device)
+    loglik = float(total[0])
     rank, _world = dist_.rank_world()
     if rank == 0:
         write_list([info["Nfeval"]] + np.asarray(arg_lst).tolist() + [loglik, time.time() - info["time"]],
