@@ -671,7 +671,26 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     ctx->launches += 1;
     // Few chains: four warps per chain (latency); many chains: one warp per chain (throughput).
     const int sms = ctx->prop.multiProcessorCount;
-    if (K <= 32 && ctx->n_blocks <= (int64_t)4 * sms && !getenv("ITR_VITERBI_1WARP")) {
+    const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "spec", "4warp", "1warp"
+    const bool want_spec = vmode ? !strcmp(vmode, "spec") : ctx->n_blocks <= (int64_t)3 * sms / 2;
+    if (K <= 32 && want_spec && !getenv("ITR_VITERBI_1WARP")) {
+        // speculate-and-verify sweep: one CTA of 16 warps per chain
+        const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);
+#define VSPEC(KT) viterbi_spec_kernel<KT><<<grid, 32 * SPEC_NW, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
+        switch ((K + 3) / 4) {
+            case 1: VSPEC(4); break;
+            case 2: VSPEC(8); break;
+            case 3: VSPEC(12); break;
+            case 4: VSPEC(16); break;
+            case 5: VSPEC(20); break;
+            case 6: VSPEC(24); break;
+            case 7: VSPEC(28); break;
+            default: VSPEC(32); break;
+        }
+#undef VSPEC
+        return;
+    }
+    if (K <= 32 && (vmode ? !strcmp(vmode, "4warp") : ctx->n_blocks <= (int64_t)4 * sms) && !getenv("ITR_VITERBI_1WARP")) {
         const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)4 * sms);
         switch ((K + 7) / 8) {
             case 1: viterbi_forward4_kernel<2><<<grid, 128, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final); break;

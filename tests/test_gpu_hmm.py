@@ -195,13 +195,15 @@ def test_reference_style_wrappers(engine):
         assert np.abs(post[i] - g[f"post_{i}"]).max() <= POST_ATOL
 
 
-@pytest.mark.parametrize("one_warp", [False, True])
-def test_viterbi_kernel_variants_agree(engine, one_warp, monkeypatch):
-    """The four-warps-per-chain sweep (few chains) and the one-warp-per-chain sweep
-    (many chains) are both bit-exact against the oracle, on near-tie-heavy data
-    (t_A == t_B makes topologies 2 and 3 exchangeable)."""
-    if one_warp:
+@pytest.mark.parametrize("variant", ["spec", "4warp", "1warp"])
+def test_viterbi_kernel_variants_agree(engine, variant, monkeypatch):
+    """The speculate-and-verify sweep (few chains), the four-warps-per-chain sweep and the
+    one-warp-per-chain sweep (many chains) are all bit-exact against the oracle, on
+    near-tie-heavy data (t_A == t_B makes topologies 2 and 3 exchangeable)."""
+    if variant == "1warp":
         monkeypatch.setenv("ITR_VITERBI_1WARP", "1")
+    else:
+        monkeypatch.setenv("ITR_VITERBI", variant)
     m = golden("model_3_3_example.npz")
     a, b, pi = m["a"], m["b"], m["pi"]
     rng = np.random.default_rng(99)
