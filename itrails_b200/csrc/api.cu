@@ -672,11 +672,19 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     // Few chains: four warps per chain (latency); many chains: one warp per chain (throughput).
     const int sms = ctx->prop.multiProcessorCount;
     const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "spec", "4warp", "1warp"
-    const bool want_spec = vmode ? !strcmp(vmode, "spec") : ctx->n_blocks <= (int64_t)3 * sms / 2;
+    // (speculation pays when backpointers are stable, i.e. on alignments dominated by a few
+    // symbols — the same test that enables run compression; else every window mispredicts)
+    const bool want_spec = vmode ? !strcmp(vmode, "spec") : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms / 2);
     if (K <= 32 && want_spec && !getenv("ITR_VITERBI_1WARP")) {
         // speculate-and-verify sweep: one CTA of 16 warps per chain
         const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);
-#define VSPEC(KT) viterbi_spec_kernel<KT><<<grid, 32 * SPEC_NW, 0, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
+        const size_t shs = (size_t)NSYM * 32 * sizeof(double);
+#define VSPEC(KT)                                                                                             \
+    do {                                                                                                      \
+        cudaFuncSetAttribute(viterbi_spec_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shs); \
+        viterbi_spec_kernel<KT><<<grid, 32 * SPEC_NW, shs, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K,    \
+                                                                 ctx->d_bp, ctx->d_final);                    \
+    } while (0)
         switch ((K + 3) / 4) {
             case 1: VSPEC(4); break;
             case 2: VSPEC(8); break;

@@ -1480,26 +1480,38 @@ __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, do
 //      the pointers are updated, and the next window starts right after it.
 // Results are bit-identical to the sequential sweep by induction over committed columns.
 // ---------------------------------------------------------------------------------
-constexpr int SPEC_W = 16, SPEC_NW = 16;
+constexpr int SPEC_W = 15, SPEC_NW = 16;       // warp 0 runs ahead, warps 1..15 verify one column each
 
 template <int KT>
 __global__ void __launch_bounds__(32 * SPEC_NW)
 viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                     const double *__restrict__ OM0, int K,
                     uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
-    constexpr int KP = 32, W = SPEC_W, NW = SPEC_NW;
-    __shared__ __align__(16) double wom[W + 1][KP];     // omega before column i of the window (speculative for i > 0)
-    __shared__ __align__(16) double rom[W][KP];         // verified omega of column i
-    __shared__ int rarg[W][KP];                         // verified first arg-maxima of column i
-    __shared__ int wsym[W];                             // symbols of the window
-    __shared__ int pcur[KP];                            // the pointers the window was run with
-    __shared__ int fail_min, chain_s;
+    constexpr int KP = 32, W = SPEC_W;
+    // Two windows in flight: while the verifiers check the pending window (buffer pb), the
+    // runner speculates the window after it into the other buffer; that speculation is
+    // dropped if the pending window turns out to hold a mismatch.
+    __shared__ __align__(16) double wom[2][W + 1][KP];  // omega before column i of a window (speculative for i > 0)
+    __shared__ __align__(16) double rom[W][KP];         // verified omega of column i of the pending window
+    __shared__ int rarg[W][KP];                         // verified first arg-maxima
+    __shared__ int mism[W];                             // column i differs from the pointers it was run with
+    __shared__ int wsym[2][W];                          // symbols of the windows
+    __shared__ int pcur[KP];                            // the pointers in use
+    __shared__ double las[KP][KP];                      // log a, for the runner's pointer lookups
+    __shared__ int chain_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_chains = cs.n_blocks;
     const int K4 = (K + 3) & ~3;
-    const double *etl = LEt + lane;
-    Cols<KT, 1, true> lacol;                            // column `lane` of log a (every warp verifies)
-    lacol.load(LA, KP, lane);
+    // the whole log-emission table lives in shared memory (625 x 32 doubles = 160 KB): with one
+    // CTA per SM the L1 left over is too small to keep the rows resident, and every lookup
+    // of the runner would otherwise pay an L2 round trip
+    extern __shared__ __align__(16) double les[];
+    for (int e = threadIdx.x; e < NSYM * KP; e += blockDim.x) les[e] = __ldg(LEt + e);
+    const double *etl = les + lane;
+    Cols<KT, 1, true> lacol;                            // column `lane` of log a (verifiers)
+    if (warp > 0) lacol.load(LA, KP, lane);
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) las[e / KP][e % KP] = __ldg(LA + e);
+    __syncthreads();
 
     for (;;) {
         if (threadIdx.x == 0) chain_s = (int)atomicAdd(cs.queue, 1u);
@@ -1512,43 +1524,58 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
         const uint16_t *symp = cs.sym + beg;            // (64 columns of slack behind the last block)
         uint8_t *bpl = bp + (size_t)beg * KP + lane;
 
-        // runner state (warp 0): pointers, their log a entries, a 32-symbol tile loaded one window ahead
+        // runner state (warp 0): pointers and their log a entries
         int p = lane;
         double la_p = __ldg(LA + (size_t)lane * KP + lane);
-        int64_t tile_base = 1;
-        unsigned tile = (unsigned)__ldg(symp + 1 + lane);
-        if (warp == 0) wom[0][lane] = __ldg(OM0 + (size_t)blk * KP + lane);
-        int64_t t = 1;                                   // first column of the next window
-        while (t < T) {
-            const int n = (int)min((int64_t)W, T - t);
-            double ew[W];                                // emission rows of the window (runner)
+        // symbols of the window the runner will most likely speculate next (the one right
+        // after the window it is speculating now), fetched a step ahead; reloaded after a mismatch
+        int64_t pre_ts = 1;
+        unsigned pre_sym = 0;
+        if (warp == 0) {
+            wom[0][0][lane] = __ldg(OM0 + (size_t)blk * KP + lane);
+            pcur[lane] = p;
+            pre_sym = (unsigned)__ldg(symp + 1 + lane);
+        }
+        int64_t tp = 1;                                  // first column not yet committed
+        int pb = 0, np_ = 0;                             // pending window: buffer, length (columns tp .. tp+np_-1)
+        int fin_b = 0, fin_i = 0;                        // where the last committed omega lives
+        __syncthreads();
+        while (tp < T) {
+            const int sb = np_ ? pb ^ 1 : pb;            // buffer the runner speculates into
+            const int64_t ts = tp + np_;                 // first column of that window
+            const int ns = (int)max((int64_t)0, min((int64_t)W, T - ts));
+            int myp = 0;
             if (warp == 0) {
-                const int o = (int)(t - tile_base);      // window symbols come from the tile loaded a window ago
-                const unsigned mysym = __shfl_sync(FULL, tile, (o + lane) & 31);
-                if (lane < W) wsym[lane] = (int)mysym;
-                pcur[lane] = p;
+                // ---- runner: omega_j = (omega_{p_j} + log a_{p_j j}) + log e_j along the window
+                if (ns > 0) {
+                    const unsigned mysym = (pre_ts == ts) ? pre_sym : (unsigned)__ldg(symp + ts + lane);
+                    if (lane < W) wsym[sb][lane] = (int)mysym;
+                    if (np_) wom[sb][0][lane] = wom[pb][np_][lane];   // continue from the pending window's (speculative) end
+                    __syncwarp();
+                    // the symbols of the window after this one: the load lands during the loop below
+                    pre_ts = ts + ns;
+                    pre_sym = (unsigned)__ldg(symp + pre_ts + lane);
+                    double ew[W];
 #pragma unroll
-                for (int i = 0; i < W; ++i) ew[i] = __ldg(etl + __shfl_sync(FULL, mysym, i) * KP);
-                tile = (unsigned)__ldg(symp + t + lane);  // serves the next window (it starts within t+1 .. t+W)
-                tile_base = t;
-                if (lane == 0) fail_min = n;
-                // ---- 1. speculative run of the window
-                double x = wom[0][p];
+                    for (int i = 0; i < W; ++i) ew[i] = etl[wsym[sb][i] * KP];
+                    // (shared-memory gathers: a 64-bit shuffle costs ~2 x 16 issue cycles on this part)
+                    double x = wom[sb][0][p];
 #pragma unroll
-                for (int i = 0; i < W; ++i) {
-                    if (i < n) {
-                        const double M = __dadd_rn(__dadd_rn(x, la_p), ew[i]);
-                        wom[i + 1][lane] = M;
-                        __syncwarp();
-                        x = wom[i + 1][p];
+                    for (int i = 0; i < W; ++i) {
+                        if (i < ns) {
+                            const double M = __dadd_rn(__dadd_rn(x, la_p), ew[i]);
+                            wom[sb][i + 1][lane] = M;      // for the verifiers and for the next column
+                            __syncwarp();
+                            x = wom[sb][i + 1][p];          // omega of each state's predecessor
+                        }
                     }
                 }
-            }
-            __syncthreads();
-            // ---- 2. exact verification, one column per warp
-            for (int i = warp; i < n; i += NW) {
-                const double le = __ldg(etl + wsym[i] * KP);
-                const double2 *x2 = reinterpret_cast<const double2 *>(&wom[i][0]);
+            } else if (warp - 1 < np_) {
+                // ---- verifiers: exact scan of column (warp - 1) of the pending window
+                const int i = warp - 1;
+                myp = pcur[lane];
+                const double le = etl[wsym[pb][i] * KP];
+                const double2 *x2 = reinterpret_cast<const double2 *>(&wom[pb][i][0]);
                 double sv[KT];
                 int ix[KT];
 #pragma unroll
@@ -1563,34 +1590,48 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
                 double M = __dadd_rn(sv[0], le);
                 int arg = ix[0];
                 if (__any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(sv[0], le, M))) {
-                    const ScanResult r = viterbi_exact_scan(&wom[i][0], LA + lane, KP, K4, le);
+                    const ScanResult r = viterbi_exact_scan(&wom[pb][i][0], LA + lane, KP, K4, le);
                     M = r.best;
                     arg = r.arg;
                 }
                 rom[i][lane] = M;
                 rarg[i][lane] = arg;
-                if (__any_sync(FULL, (lane < K) & (arg != pcur[lane])) && lane == 0) atomicMin(&fail_min, i);
+                const bool bad = __any_sync(FULL, (lane < K) & (arg != myp));
+                if (lane == 0) mism[i] = bad ? 1 : 0;
             }
             __syncthreads();
-            // ---- 3. commit
-            const int f = fail_min;                      // first mismatching column of the window (n if none)
-            for (int i = warp; i < min(f, n); i += NW) bpl[(size_t)(t + i) * KP] = (uint8_t)pcur[lane];
-            if (warp == 0) {
-                if (f < n) {
+            // ---- everyone: first mismatching column of the pending window (np_ if none); commit
+            const unsigned bad = __ballot_sync(FULL, lane < np_ && mism[lane]);
+            const int f = bad ? __ffs(bad) - 1 : np_;
+            if (warp > 0 && warp - 1 < f) bpl[(size_t)(tp + warp - 1) * KP] = (uint8_t)myp;
+            if (f < np_) {
+                // mismatch: column f takes the verifier's result; the speculation beyond it is dropped
+                if (warp == 0) {
                     p = rarg[f][lane];
-                    la_p = __ldg(LA + (size_t)p * KP + lane);
-                    bpl[(size_t)(t + f) * KP] = (uint8_t)p;
-                    wom[0][lane] = rom[f][lane];
-                } else {
-                    wom[0][lane] = wom[n][lane];
+                    la_p = las[p][lane];
+                    bpl[(size_t)(tp + f) * KP] = (uint8_t)p;
+                    wom[0][0][lane] = rom[f][lane];
+                    pcur[lane] = p;
                 }
+                tp += f + 1;
+                pb = 0;
+                np_ = 0;
+                fin_b = 0;
+                fin_i = 0;
+            } else {
+                if (np_) {
+                    fin_b = pb;
+                    fin_i = np_;
+                }
+                tp += np_;
+                pb = sb;
+                np_ = ns;
             }
-            t += (f < n) ? f + 1 : n;
             __syncthreads();
         }
         if (warp == 0) {
-            // first argmax of omega_{T-1}
-            const double om = wom[0][lane];
+            // first argmax of omega_{T-1}: the last committed omega
+            const double om = wom[fin_b][fin_i][lane];
             double best = (lane < K) ? om : -CUDART_INF;
             int bidx = (lane < K) ? lane : 0x7fffffff;
 #pragma unroll
