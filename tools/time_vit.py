@@ -2,6 +2,9 @@ import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from itrails_b200 import _lib
+if os.environ.get('ITR_LIB'):
+    _lib.LIB_PATH = os.path.abspath(os.environ['ITR_LIB'])
 import itrails_b200 as itb
 from itrails_b200 import synth
 from itrails_b200.optimizer import viterbi_tables
