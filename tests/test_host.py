@@ -376,3 +376,73 @@ def test_write_maf_roundtrip(tmp_path):
     assert len(back) == 3 and all(np.array_equal(x, y) for x, y in zip(back, V_lst))
     co = itb.parse_coordinates(str(p), ["hg38", "panTro5", "gorGor5", "ponAbe2"], "hg38")
     assert len(co[1]) == 50
+
+
+def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
+    """The reference-style wrappers under torch.distributed (gloo, 2 ranks, CPU): every
+    rank loads only its LPT share of the blocks, the log-likelihood is all-reduced to the
+    full sum, the decoders return the rank's own blocks, and only rank 0 writes the
+    optimiser's files.  The GPU engine is replaced by a stand-in that answers with the
+    oracle, so this covers the host logic of the N > 1 path."""
+    script = tmp_path / "w2.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "oracle"))
+        import numpy as np, torch.distributed as dist, yaml
+        import hmm_oracle as ho, ctmc_oracle as co
+        from itrails_b200 import distributed as D, engine_cache, optimizer as opt_mod
+        import itrails_b200.optimizer as O
+
+        class FakeEngine:
+            device = 0
+            def load_blocks(self, V_lst): self.V = list(V_lst); self.loads = getattr(self, "loads", 0) + 1
+            def set_model(self, a, b, pi): self.m = (a, b, pi)
+            def build_model(self, params, n_ab, n_abc, cut_AB=None, cut_ABC=None, fetch=True):
+                a, b, pi, hid, _ = co.trans_emiss_calc(*params[0], n_ab, n_abc)
+                self.m = (a, b, pi)
+                return None, None, None, None
+            def loglik(self): return np.array([ho.loglik_wrapper(*self.m, self.V)])
+            def viterbi(self, log_a, log_E, omega0):
+                return np.concatenate([p for p in ho.viterbi_wrapper(*self.m, self.V)]).astype(np.uint8)
+            def split(self, flat):
+                off = np.cumsum([0] + [len(v) for v in self.V]); return [flat[off[i]:off[i + 1]] for i in range(len(self.V))]
+        engine_cache._ENGINE = FakeEngine()
+
+        dist.init_process_group("gloo")
+        rank = dist.get_rank()
+        g = np.load(os.path.join({ROOT!r}, "tests", "golden", "model_1_1_example.npz"))
+        a, b, pi = g["a"], g["b"], g["pi"]
+        rng = np.random.default_rng(1)
+        V_lst = [rng.integers(0, 256, size=int(n)) for n in rng.integers(5, 60, size=9)]
+        ll = O.loglik_wrapper(a, b, pi, V_lst)
+        want = ho.loglik_wrapper(a, b, pi, V_lst)
+        assert abs(ll - want) <= 1e-12 * abs(want), (ll, want)
+        ll2 = O.loglik_wrapper(a, b, pi, V_lst)            # second call: blocks stay resident
+        assert engine_cache._ENGINE.loads == 1 and ll2 == ll
+        mine = D.lpt_partition([len(v) for v in V_lst], 2)[rank]
+        assert [len(v) for v in engine_cache._ENGINE.V] == [len(V_lst[i]) for i in mine]
+        paths = O.viterbi_wrapper(a, b, pi, V_lst)
+        ref = ho.viterbi_wrapper(a, b, pi, V_lst)
+        assert len(paths) == len(mine) and all(np.array_equal(p, ref[i]) for p, i in zip(paths, mine))
+        # objective: rank 0 alone writes the history / best-model files
+        d = dict(zip(("t_A", "t_B", "t_C", "t_2", "t_upper", "t_out", "N_AB", "N_ABC", "r"), g["args"]))
+        d.update(n_int_AB=1, n_int_ABC=1)
+        res = os.path.join({str(tmp_path)!r}, "run")
+        if rank == 0:
+            with open(res + ".best_model.yaml", "w") as fh:
+                yaml.dump({{"fixed_parameters": {{"mu": 1e-8}}, "optimized_parameters": {{}},
+                           "results": {{"log_likelihood": None, "iteration": None}}}}, fh)
+        dist.barrier()
+        val = O.optimization_wrapper([d["N_AB"]], ["N_AB"], frozenset(["t_A", "t_B", "t_C"]), d, V_lst, res, {{"Nfeval": 0, "time": 0.0}})
+        assert abs(-val - want) <= 1e-9 * abs(want), (val, want)
+        dist.barrier()
+        if rank == 0:
+            lines = open(res + ".optimization_history.csv").read().strip().splitlines()
+            assert len(lines) == 1 and lines[0].startswith("0,")
+        print("rank", rank, "ok")
+    """))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
