@@ -568,6 +568,9 @@ forward_runs_kernel(ChainSet cs, const double *__restrict__ A, const double *__r
 // (optimizer.py:210); in a run that is beta_{t+n} (diag(e) a)^n.
 // ---------------------------------------------------------------------------------
 constexpr int PTILE = 32;
+#ifndef ITR_TILES_MINB
+#define ITR_TILES_MINB 1
+#endif
 
 // DIR 0: forward checkpoints ck[tile] = alpha_{32 m - 1} (state entering tile m; tile 0 unused)
 // DIR 1: backward checkpoints ck[tile] = beta_{32 m + 31} (last tile of a block: not stored, it is 1)
@@ -698,7 +701,7 @@ checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double 
 
 // Pass 2: one warp per tile.  al: forward vectors of the tile, stride KP + 1.
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, ITR_TILES_MINB)
 posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
                        const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
                        int64_t g_begin, int64_t g_end, const double *__restrict__ A, const double *__restrict__ PI,
@@ -713,6 +716,22 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
     const double *etl = Et + lane;
     Cols<KT, 1, true> acol;
     acol.load(A, KP, lane);
+    // y_lane = sum_i xv[i] * a[i][lane]: this kernel is throughput bound (many warps per
+    // scheduler), so the loads are left to the compiler's streaming schedule instead of the
+    // register-hungry fenced groups of matvec<>
+    auto dot = [&](const double *xv) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(xv);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int i = 0; i < KT; i += 4) {
+            const double2 p = x2[i / 2], q = x2[i / 2 + 1];
+            a0 = fma(p.x, acol.c[i], a0);
+            a1 = fma(p.y, acol.c[i + 1], a1);
+            a2 = fma(q.x, acol.c[i + 2], a2);
+            a3 = fma(q.y, acol.c[i + 3], a3);
+        }
+        return (a0 + a1) + (a2 + a3);
+    };
 
     for (int64_t g = g_begin + (int64_t)blockIdx.x * nwarps + warp; g < g_end; g += (int64_t)gridDim.x * nwarps) {
         const int blk = tile_blk[g];
@@ -740,9 +759,7 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
             buf ^= 1;
             xb[lane] = x[0];
             __syncwarp();
-            double y[1];
-            matvec<KT, 1, true>(xb, acol, KT, y);
-            x[0] = y[0] * e;
+            x[0] = dot(xb) * e;
             if ((i & 7) == 7) (void)rescale_pow2<1>(x);
             al[i * LD + lane] = x[0];
         }
@@ -757,9 +774,7 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
             buf ^= 1;
             xb[lane] = b[0] * e;
             __syncwarp();
-            double y[1];
-            matvec<KT, 1, true>(xb, acol, KT, y);
-            b[0] = y[0];
+            b[0] = dot(xb);
             if ((i & 7) == 0) (void)rescale_pow2<1>(b);
         }
         __syncwarp();
