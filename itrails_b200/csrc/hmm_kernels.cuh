@@ -1509,7 +1509,7 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
     __shared__ __align__(16) double wom[2][W + 1][KP];  // omega before column i of a window (speculative for i > 0)
     __shared__ __align__(16) double rom[W][KP];         // verified omega of column i of the pending window
     __shared__ int rarg[W][KP];                         // verified first arg-maxima
-    __shared__ int mism[W];                             // column i differs from the pointers it was run with
+    __shared__ int mism[2][W];                          // column i differs from the runner's choice (by step parity)
     __shared__ int wsym[2][W];                          // symbols of the windows
     __shared__ int wptr[2][W][KP];                      // the pointer the runner chose for each column
     __shared__ double las[KP][KP];                      // log a, for the runner's pointer lookups
@@ -1557,6 +1557,7 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
         int64_t tp = 1;                                  // first column not yet committed
         int pb = 0, np_ = 0;                             // pending window: buffer, length (columns tp .. tp+np_-1)
         int fin_b = 0, fin_i = 0;                        // where the last committed omega lives
+        int par = 0;                                     // step parity (double-buffers `mism`)
         __syncthreads();
         while (tp < T) {
             const int sb = np_ ? pb ^ 1 : pb;            // buffer the runner speculates into
@@ -1620,11 +1621,12 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
                 rom[i][lane] = M;
                 rarg[i][lane] = arg;
                 const bool bad = __any_sync(FULL, (lane < K) & (arg != myp));
-                if (lane == 0) mism[i] = bad ? 1 : 0;
+                if (lane == 0) mism[par][i] = bad ? 1 : 0;
             }
             __syncthreads();
             // ---- everyone: first mismatching column of the pending window (np_ if none); commit
-            const unsigned bad = __ballot_sync(FULL, lane < np_ && mism[lane]);
+            const unsigned bad = __ballot_sync(FULL, lane < np_ && mism[par][lane]);
+            par ^= 1;
             const int f = bad ? __ffs(bad) - 1 : np_;
             if (warp > 0 && warp - 1 < f) bpl[(size_t)(tp + warp - 1) * KP] = (uint8_t)myp;
             if (f < np_) {
@@ -1654,7 +1656,10 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
                 pb = sb;
                 np_ = ns;
             }
-            __syncthreads();
+            // One barrier per step suffices: what the next step writes (the other window
+            // buffer, `mism` of the other parity, rom/rarg only when a window is pending) is
+            // never read again by this one, and after a mismatch the verifiers sit the next
+            // step out while warp 0 alone touches what it just repaired.
         }
         if (warp == 0) {
             // first argmax of omega_{T-1}: the last committed omega
