@@ -40,7 +40,8 @@ enum itr_status {
     ITR_ERR_STATE = -2,    /* call order violated (e.g. loglik before set_model) */
     ITR_ERR_CUDA = -3,     /* CUDA runtime error / no usable device            */
     ITR_ERR_NOMEM = -4,    /* host or device allocation failed                 */
-    ITR_ERR_UNSUPPORTED = -5
+    ITR_ERR_UNSUPPORTED = -5,
+    ITR_ERR_IO = -6        /* a file could not be opened / written              */
 };
 
 #define ITR_N_SYMBOLS 625   /* read_data.py:6-24 */
@@ -143,6 +144,9 @@ int itr_loglik(itr_ctx *ctx, double *total, double *per_block);
 int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_E,
                 const double *omega0, uint8_t *path);
 int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path);
+/* Columns [col0, col0 + n_cols) of the concatenated path kept on the device: lets a
+ * writer stream a chromosome-scale result block by block (workflow_viterbi.py:692-743). */
+int itr_viterbi_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, uint8_t *path);
 
 /* Posterior decoding of every block with parameter set 0.  Replaces
  * post_prob_wrapper (optimizer.py:241-262), including the reference's backward
@@ -151,6 +155,28 @@ int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path);
  * (see itr_posterior_fetch). */
 int itr_posterior(itr_ctx *ctx, double *post);
 int itr_posterior_fetch(itr_ctx *ctx, double *post);
+/* Rows [col0, col0 + n_cols) of the posterior matrix kept on the device (n_cols x K
+ * doubles): the 250 Mb x 27 result is 54 GB and is consumed block by block by the
+ * CSV writer (workflow_posterior.py:697-716). */
+int itr_posterior_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, double *post);
+
+/* ---- result writers (host C++, thread pool) --------------------------------------
+ * Write `{prefix}.posterior.csv` exactly as the reference's csv.writer loop does
+ * (workflow_posterior.py:697-716): header `alignment_block_idx,position_idx,prob_state_0…`,
+ * one row per column, "\r\n" line ends, integers in decimal, probabilities as Python's
+ * repr(float) (shortest round-trip digits; exponent form iff the decimal exponent is
+ * < -4 or >= 16) — byte-identical files.  positions (nullable) holds one int64 per
+ * column of the loaded alignment (the reference coordinates of parse_coordinates);
+ * NULL writes 0..T-1 within every block.  n_threads <= 0 uses every host core.
+ * itr_posterior_write_csv streams the posterior kept on the device by the last
+ * itr_posterior block by block (download of block i+1 overlaps formatting of block i), so
+ * a chromosome-scale result never has to exist in host memory. */
+int itr_posterior_write_csv(itr_ctx *ctx, const char *path, const int64_t *positions, int n_threads);
+/* The same writer on a host matrix (no GPU context needed): post is sum(T) x K. */
+int itr_csv_posterior_host(const char *path, int K, int64_t n_blocks, const int64_t *offsets,
+                           const int64_t *positions, const double *post, int n_threads);
+/* repr(float) of one value into out (cap >= 32, NUL terminated); returns the length. */
+int itr_csv_format_double(double x, char *out, int cap);
 
 /* ---- overlapping the recursions ---------------------------------------------------
  * Every recursion runs on its own CUDA stream.  By default each call returns when its

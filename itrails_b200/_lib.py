@@ -22,7 +22,7 @@ class ItrailsCudaError(ItrailsError):
     """The CUDA library or device is missing/unusable.  There is no CPU fallback."""
 
 
-ITR_ERR_ARG, ITR_ERR_STATE, ITR_ERR_CUDA, ITR_ERR_NOMEM, ITR_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+ITR_ERR_ARG, ITR_ERR_STATE, ITR_ERR_CUDA, ITR_ERR_NOMEM, ITR_ERR_UNSUPPORTED, ITR_ERR_IO = -1, -2, -3, -4, -5, -6
 PHASES = {"loglik": 0, "viterbi_fwd": 1, "viterbi_trace": 2, "post_fwd": 3, "post_bwd": 4,
           "model": 5, "emit_table": 6, "post_combine": 7, "post_total": 8}
 
@@ -49,8 +49,13 @@ SIGNATURES = {
     "itr_loglik": (ctypes.c_int, [_c_ctx, _dp, _dp]),
     "itr_viterbi": (ctypes.c_int, [_c_ctx, _dp, _dp, _dp, _u8p]),
     "itr_viterbi_fetch": (ctypes.c_int, [_c_ctx, _u8p]),
+    "itr_viterbi_fetch_range": (ctypes.c_int, [_c_ctx, ctypes.c_int64, ctypes.c_int64, _u8p]),
     "itr_posterior": (ctypes.c_int, [_c_ctx, _dp]),
     "itr_posterior_fetch": (ctypes.c_int, [_c_ctx, _dp]),
+    "itr_posterior_fetch_range": (ctypes.c_int, [_c_ctx, ctypes.c_int64, ctypes.c_int64, _dp]),
+    "itr_posterior_write_csv": (ctypes.c_int, [_c_ctx, ctypes.c_char_p, _i64p, ctypes.c_int]),
+    "itr_csv_posterior_host": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int64, _i64p, _i64p, _dp, ctypes.c_int]),
+    "itr_csv_format_double": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p, ctypes.c_int]),
     "itr_set_async": (ctypes.c_int, [_c_ctx, ctypes.c_int]),
     "itr_sync": (ctypes.c_int, [_c_ctx]),
     "itr_maf_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.c_int,
@@ -109,6 +114,8 @@ def check(lib, ctx, rc):
         raise ItrailsCudaError(rc, msg)
     if rc == ITR_ERR_NOMEM:
         raise MemoryError(msg)
+    if rc == ITR_ERR_IO:
+        raise OSError(msg or "file could not be written")
     raise ItrailsError(rc, msg)
 
 

@@ -23,6 +23,7 @@
 
 #include "hmm_kernels.cuh"
 #include "model_build.h"
+#include "csv_writer.h"
 #include "model_plan.h"
 
 using namespace itr;
@@ -926,6 +927,19 @@ extern "C" int itr_viterbi_fetch(itr_ctx *ctx, uint8_t *path) {
     return ITR_OK;
 }
 
+extern "C" int itr_viterbi_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, uint8_t *path) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!path && n_cols > 0) return fail(ctx, ITR_ERR_ARG, "itr_viterbi_fetch_range: path is NULL");
+    if (!ctx->have_path) return fail(ctx, ITR_ERR_STATE, "itr_viterbi_fetch_range: no Viterbi result on the device");
+    if (col0 < 0 || n_cols < 0 || col0 + n_cols > ctx->n_cols)
+        return fail(ctx, ITR_ERR_ARG, "itr_viterbi_fetch_range: column range outside the loaded alignment");
+    if (n_cols == 0) return ITR_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(path, ctx->d_path + col0, (size_t)n_cols, cudaMemcpyDeviceToHost, ctx->s_vit));
+    CK(cudaStreamSynchronize(ctx->s_vit));
+    return ITR_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // posterior
 // ---------------------------------------------------------------------------------
@@ -1119,4 +1133,72 @@ extern "C" int itr_posterior_fetch(itr_ctx *ctx, double *post) {
     CK(cudaMemcpyAsync(post, ctx->d_post, (size_t)ctx->n_cols * ctx->K * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_post));
     CK(cudaStreamSynchronize(ctx->s_post));
     return ITR_OK;
+}
+
+extern "C" int itr_posterior_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, double *post) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!post && n_cols > 0) return fail(ctx, ITR_ERR_ARG, "itr_posterior_fetch_range: post is NULL");
+    if (!ctx->have_post) return fail(ctx, ITR_ERR_STATE, "itr_posterior_fetch_range: no posterior on the device");
+    if (col0 < 0 || n_cols < 0 || col0 + n_cols > ctx->n_cols)
+        return fail(ctx, ITR_ERR_ARG, "itr_posterior_fetch_range: column range outside the loaded alignment");
+    if (n_cols == 0) return ITR_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(post, ctx->d_post + (size_t)col0 * ctx->K, (size_t)n_cols * ctx->K * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->s_post));
+    CK(cudaStreamSynchronize(ctx->s_post));
+    return ITR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// posterior CSV straight from the device result (workflow_posterior.py:697-716)
+// ---------------------------------------------------------------------------------
+extern "C" int itr_posterior_write_csv(itr_ctx *ctx, const char *path, const int64_t *positions, int n_threads) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!path) return fail(ctx, ITR_ERR_ARG, "itr_posterior_write_csv: path is NULL");
+    if (!ctx->have_post) return fail(ctx, ITR_ERR_STATE, "itr_posterior_write_csv: no posterior on the device");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_post));
+    const int K = ctx->K;
+    const int64_t nb = ctx->n_blocks;
+    int64_t max_len = 0;
+    for (int64_t i = 0; i < nb; ++i) max_len = std::max(max_len, ctx->h_off[i + 1] - ctx->h_off[i]);
+    itr::PosteriorCsv w;
+    std::string err;
+    if (!w.open(path, K, n_threads, err)) return fail(ctx, ITR_ERR_IO, "itr_posterior_write_csv: %s", err.c_str());
+    double *h[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = ITR_OK;
+    auto cleanup = [&]() {
+        for (int q = 0; q < 2; ++q) {
+            if (h[q]) cudaFreeHost(h[q]);
+            if (ev[q]) cudaEventDestroy(ev[q]);
+        }
+    };
+    for (int q = 0; q < 2 && rc == ITR_OK; ++q) {
+        if (cudaMallocHost(&h[q], (size_t)max_len * K * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(ctx, ITR_ERR_NOMEM, "itr_posterior_write_csv: cannot page-lock %zu bytes", (size_t)max_len * K * sizeof(double));
+        } else if (cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming) != cudaSuccess) {
+            rc = fail(ctx, ITR_ERR_CUDA, "itr_posterior_write_csv: cudaEventCreate failed");
+        }
+    }
+    auto fetch = [&](int64_t i) -> cudaError_t {
+        const int64_t c0 = ctx->h_off[i], n = ctx->h_off[i + 1] - c0;
+        cudaError_t e = cudaMemcpyAsync(h[i & 1], ctx->d_post + (size_t)c0 * K, (size_t)n * K * sizeof(double),
+                                        cudaMemcpyDeviceToHost, ctx->stream2);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], ctx->stream2);
+        return e;
+    };
+    if (rc == ITR_OK && nb > 0 && fetch(0) != cudaSuccess) rc = fail(ctx, ITR_ERR_CUDA, "itr_posterior_write_csv: download failed");
+    for (int64_t i = 0; i < nb && rc == ITR_OK; ++i) {
+        if (cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { rc = fail(ctx, ITR_ERR_CUDA, "itr_posterior_write_csv: download failed"); break; }
+        if (i + 1 < nb && fetch(i + 1) != cudaSuccess) { rc = fail(ctx, ITR_ERR_CUDA, "itr_posterior_write_csv: download failed"); break; }
+        const int64_t c0 = ctx->h_off[i], n = ctx->h_off[i + 1] - c0;
+        if (!w.write_block(i, positions ? positions + c0 : nullptr, h[i & 1], n, err))
+            rc = fail(ctx, ITR_ERR_IO, "itr_posterior_write_csv: %s", err.c_str());
+    }
+    cudaStreamSynchronize(ctx->stream2);
+    cleanup();
+    if (!w.close() && rc == ITR_OK) rc = fail(ctx, ITR_ERR_IO, "itr_posterior_write_csv: close failed");
+    return rc;
 }

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -159,6 +160,35 @@ class Engine:
             out = np.empty((self.n_columns, self.K))
         self._ck(self._lib.itr_posterior(self._ctx, L.as_ptr(out, ctypes.c_double) if fetch else None))
         return out if fetch else None
+
+    def posterior_block(self, i, out=None):
+        """Posterior matrix (T_i, K) of block ``i`` from the result kept on the device."""
+        off = self._offsets
+        c0, n = int(off[i]), int(off[i + 1] - off[i])
+        if out is None:
+            out = np.empty((n, self.K))
+        self._ck(self._lib.itr_posterior_fetch_range(self._ctx, c0, n, L.as_ptr(out, ctypes.c_double)))
+        return out
+
+    def write_posterior_csv(self, path, positions=None, n_threads=0):
+        """``{prefix}.posterior.csv`` (workflow_posterior.py:697-716) written by the native
+        writer straight from the posterior kept on the device; ``positions`` = one int64
+        per column (reference coordinates) or None for 0..T-1 within each block."""
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=np.int64)
+            if positions.shape != (self.n_columns,):
+                raise ValueError("positions must hold one entry per alignment column")
+        self._ck(self._lib.itr_posterior_write_csv(self._ctx, os.fsencode(path),
+                                                   L.as_ptr(positions, ctypes.c_int64), int(n_threads)))
+
+    def viterbi_block(self, i, out=None):
+        """uint8 state path of block ``i`` from the result kept on the device."""
+        off = self._offsets
+        c0, n = int(off[i]), int(off[i + 1] - off[i])
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.itr_viterbi_fetch_range(self._ctx, c0, n, L.as_ptr(out, ctypes.c_uint8)))
+        return out
 
     def split(self, flat):
         """Concatenated per-column result -> list of per-block views."""

@@ -104,6 +104,22 @@ def post_prob_wrapper(a, b, pi, V_lst):
     return eng.split(post)
 
 
+def post_prob_to_csv(a, b, pi, V_lst, output_file, ref_coordinates=None, n_threads=0):
+    """Posterior decoding written straight to ``output_file`` in the reference's format
+    (workflow_posterior.py:697-716) without materialising the list of (T, K) matrices on
+    the host: the result stays in HBM and the native writer streams it block by block.
+    Byte-identical to ``csv.writer`` over ``post_prob_wrapper``'s result."""
+    eng, local = _resident(V_lst)
+    eng.set_model(a, b, pi)
+    positions = None
+    if ref_coordinates is not None:
+        if [len(c) for c in ref_coordinates] != [len(v) for v in local]:
+            raise IndexError("reference coordinates do not match the alignment blocks")
+        positions = np.concatenate([np.asarray(c, dtype=np.int64) for c in ref_coordinates])
+    eng.posterior(fetch=False)
+    eng.write_posterior_csv(output_file, positions, n_threads)
+
+
 def viterbi_wrapper(a, b, pi, V_lst):
     """List of float64 state paths, one per block (optimizer.py:357-377; the reference
     returns float arrays, e.g. ``14.0``)."""

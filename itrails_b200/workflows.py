@@ -393,7 +393,7 @@ def viterbi_segments(res, coords=None):
 
 def _decode_main(what, argv):
     from .get_trans_emiss import trans_emiss_calc
-    from .optimizer import post_prob_wrapper, viterbi_wrapper
+    from .optimizer import post_prob_to_csv, post_prob_wrapper, viterbi_wrapper
     from .read_data import maf_parser, parse_coordinates
 
     parser = _decode_parser(what)
@@ -478,6 +478,14 @@ def _decode_main(what, argv):
         print(f"Viterbi decoding complete. Results saved to {output_file}.")
     else:
         print("Running posterior decoding.")
+        from . import distributed as dist_
+        native = not dist_.is_active() and os.environ.get("ITRAILS_PY_CSV") is None and (
+            ref_coordinates is None or [len(c) for c in ref_coordinates] == [len(v) for v in maf_alignment])
+        if native:
+            print("Writing results to file.")
+            post_prob_to_csv(a, b, pi, maf_alignment, output_file, ref_coordinates, settings.get("n_cpu") or 0)
+            print(f"Posterior decoding complete. Results saved to {output_file}.")
+            return output_file
         result = post_prob_wrapper(a=a, b=b, pi=pi, V_lst=maf_alignment)
         print("Writing results to file.")
         with open(output_file, "w", newline="") as fh:

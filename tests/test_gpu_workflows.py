@@ -76,5 +76,17 @@ def test_optimize_then_decode(small_maf, engine):
     assert len(rows) == 1 + sum(len(v) for v in V_lst)
     probs = np.array(rows[1:4001], dtype=float)[:, 2:]
     np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-9)
+    # the native streaming writer and the reference's csv.writer loop give the same bytes
+    for extra in ([], ["--reference", "hg38"]):
+        prefix2 = os.path.join(d, "out", "cmp" + str(len(extra)))
+        out_native = workflows.posterior_main(["--config-file", prefix + ".best_model.yaml", "--input", maf,
+                                               "--output", prefix2 + "_native"] + extra)
+        os.environ["ITRAILS_PY_CSV"] = "1"
+        try:
+            out_py = workflows.posterior_main(["--config-file", prefix + ".best_model.yaml", "--input", maf,
+                                               "--output", prefix2 + "_py"] + extra)
+        finally:
+            del os.environ["ITRAILS_PY_CSV"]
+        assert open(out_native, "rb").read() == open(out_py, "rb").read()
     engine_cache._ENGINE = None
     engine_cache._LOADED = None

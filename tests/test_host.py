@@ -446,3 +446,45 @@ def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_native_posterior_csv_is_byte_identical_to_csv_writer(tmp_path):
+    """itr_csv_posterior_host / itr_csv_format_double (host C++, no GPU) against Python's
+    csv.writer + repr(float), which is what workflow_posterior.py:697-716 produces."""
+    import csv
+    import ctypes
+    import io
+    from itrails_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(64)
+    rng = np.random.default_rng(5)
+    vals = [0.0, -0.0, 1.0, 0.1, 1e-4, 1e-5, 9.999e-5, 1e15, 1e16, 1.5e16, 9999999999999998.0, 1e22, 1e23, 5e-324,
+            2.2250738585072014e-308, 1.7976931348623157e308, float("inf"), -float("inf"), 1 / 3, 1e-7, 1e100, 1e-100]
+    vals += list(rng.random(20000)) + list(np.exp(rng.uniform(-700, 700, 20000)))
+    vals += [v for v in np.frombuffer(rng.bytes(8 * 20000), dtype=np.float64) if v == v]
+    for v in vals:
+        n = lib.itr_csv_format_double(float(v), buf, 64)
+        assert buf.value.decode() == repr(float(v)) and n == len(repr(float(v)))
+    assert lib.itr_csv_format_double(1.0, buf, 8) < 0
+    K, lens = 27, [5, 1, 4097, 9000]
+    off = np.zeros(len(lens) + 1, np.int64)
+    off[1:] = np.cumsum(lens)
+    post = rng.random((off[-1], K)) ** 8
+    post /= post.sum(1, keepdims=True)
+    post[3, :] = 0
+    post[3, 2] = 1.0
+    post[10, 5] = 1e-300
+    pos = rng.integers(-9, 10**9, off[-1]).astype(np.int64)
+    for positions in (None, pos):
+        p = str(tmp_path / "x.csv")
+        rc = lib.itr_csv_posterior_host(p.encode(), K, len(lens), _lib.as_ptr(off, ctypes.c_int64),
+                                        _lib.as_ptr(positions, ctypes.c_int64), _lib.as_ptr(post, ctypes.c_double), 3)
+        assert rc == 0
+        s = io.StringIO(newline="")
+        w = csv.writer(s)
+        w.writerow(["alignment_block_idx", "position_idx"] + [f"prob_state_{i}" for i in range(K)])
+        for bi in range(len(lens)):
+            for r in range(off[bi], off[bi + 1]):
+                w.writerow([bi, int(pos[r]) if positions is not None else r - off[bi]] + post[r].tolist())
+        assert open(p, "rb").read() == s.getvalue().encode()
+    assert lib.itr_csv_posterior_host(str(tmp_path / "no" / "dir.csv").encode(), K, 0, None, None, None, 1) == _lib.ITR_ERR_IO
