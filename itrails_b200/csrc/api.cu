@@ -335,17 +335,22 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     // sweep is worth using — are most columns covered by a handful of symbols?
     if (!ctx->d_hist) {
         CK(cudaMalloc((void **)&ctx->d_rep, NSYM * sizeof(int32_t)));
-        CK(cudaMalloc((void **)&ctx->d_hist, NSYM * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&ctx->d_hist, (NSYM + 1) * sizeof(unsigned long long)));
         CK(cudaMalloc((void **)&ctx->d_isrun, 640));
         CK(cudaMalloc((void **)&ctx->d_runinfo, 2 * sizeof(long long)));
     }
-    CK(cudaMemsetAsync(ctx->d_hist, 0, NSYM * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_hist, 0, (NSYM + 1) * sizeof(unsigned long long), ctx->stream));
     symbol_hist_kernel<<<std::min<unsigned>(blocks_for((size_t)n_cols, 256), 4u * ctx->prop.multiProcessorCount), 256, 0, ctx->stream>>>(
         ctx->d_sym, n_cols, ctx->d_hist);
     ctx->launches += 1;
-    std::vector<unsigned long long> hist(NSYM);
-    CK(cudaMemcpyAsync(hist.data(), ctx->d_hist, NSYM * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> hist(NSYM + 1);
+    CK(cudaMemcpyAsync(hist.data(), ctx->d_hist, (NSYM + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (hist[NSYM]) {                    // validated on the device; name the first offender
+        for (int64_t i = 0; i < n_cols; ++i)
+            if (sym[i] >= NSYM) return fail(ctx, ITR_ERR_ARG, "symbol %u at column %lld is outside 0..624", sym[i], (long long)i);
+    }
+    hist.pop_back();
     CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
     std::partial_sort(hist.begin(), hist.begin() + 4, hist.end(), std::greater<unsigned long long>());
     ctx->use_runs = 2 * (hist[0] + hist[1] + hist[2] + hist[3]) > (unsigned long long)n_cols;
@@ -385,13 +390,7 @@ extern "C" int itr_load_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t 
     if (!sym) return fail(ctx, ITR_ERR_ARG, "sym is NULL");
     int rc = check_offsets(ctx, off, n_blocks);
     if (rc) return rc;
-    const int64_t n = off[n_blocks];
-    uint16_t mx = 0;
-    for (int64_t i = 0; i < n; ++i) mx = std::max(mx, sym[i]);          // vectorised by the compiler
-    if (mx >= NSYM)
-        for (int64_t i = 0; i < n; ++i)
-            if (sym[i] >= NSYM) return fail(ctx, ITR_ERR_ARG, "symbol %u at column %lld is outside 0..624", sym[i], (long long)i);
-    return install_blocks(ctx, sym, off, n_blocks);
+    return install_blocks(ctx, sym, off, n_blocks);      // symbols are range-checked on the device
 }
 
 extern "C" int itr_load_blocks_i64(itr_ctx *ctx, const int64_t *sym, const int64_t *off, int64_t n_blocks) {
@@ -964,17 +963,18 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         phase_begin(ctx, ITR_PH_POST_TOTAL, st);
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        const Geometry g = geometry(ctx, ctx->n_blocks, 12);
-        const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-        const ChainSet csb = chain_set(ctx, 1, 1), csf = chain_set(ctx, 1, 3);
-        cudaMemsetAsync(csb.queue, 0, sizeof(unsigned int), ctx->stream2);
-        cudaMemsetAsync(csf.queue, 0, sizeof(unsigned int), st);
         const int wt = 4;
         const size_t sht = (size_t)wt * (2 * KP + PTILE * (KP + 1) + PTILE) * sizeof(double);
-        // Pass 2 runs in slices of consecutive tiles (= consecutive columns); with a host
-        // destination every slice is downloaded on a copy stream while the next one computes.
-        const int n_slices = post ? (int)std::min<int64_t>(std::min<int64_t>(8, ctx->n_blocks), std::max<int64_t>(1, ctx->n_tiles / 4096)) : 1;
-        if (post && ctx->grp_streams.empty()) {
+        // Device destination: one pair of sweeps over all blocks, then one pass-2 launch.
+        // Host destination: blocks are independent, so they run in groups of similar
+        // length (contiguous ranges of the longest-first order), shortest group first,
+        // each group's sweeps on its own pair of streams; as soon as a group's
+        // checkpoints exist its blocks go through pass 2 and are downloaded on a copy
+        // stream — the 2 GB PCIe transfer starts after the SHORTEST blocks' sweeps and
+        // hides the long blocks' latency-bound sweeps.
+        const int nb = (int)ctx->n_blocks;
+        const int n_groups = post ? std::min(8, std::max(1, nb / 2)) : 1;
+        while (post && (int)ctx->grp_streams.size() < 2 * 8 + 1) {
             cudaStream_t s2 = nullptr;
             cudaEvent_t e2 = nullptr;
             CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -982,45 +982,79 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
             CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
             ctx->grp_events.push_back(e2);
         }
-        std::vector<int64_t> slice_tile(n_slices + 1), slice_col(n_slices + 1);
-        for (int q = 0; q <= n_slices; ++q) {
-            // slice boundaries on block boundaries keep the tile <-> column mapping trivial
-            const int64_t b = ctx->n_blocks * q / n_slices;
-            slice_col[q] = ctx->h_off[b];
-            slice_tile[q] = ctx->h_tile_off[b];
-        }
-        cudaStream_t scopy = post ? ctx->grp_streams[0] : nullptr;
-        cudaEvent_t ecopy = post ? ctx->grp_events[0] : nullptr;
+        cudaStream_t scopy = post ? ctx->grp_streams[16] : nullptr;
+        cudaEvent_t ecopy = post ? ctx->grp_events[16] : nullptr;
 #define POST2(KT)                                                                                                     \
     do {                                                                                                              \
-        phase_begin(ctx, ITR_PH_POST_BWD, ctx->stream2);                                                              \
-        checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, ctx->stream2>>>(                                   \
-            csb, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
-        phase_end(ctx, ITR_PH_POST_BWD, ctx->stream2);                                                                \
-        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));                                                              \
-        phase_begin(ctx, ITR_PH_POST_FWD, st);                                                                        \
-        checkpoint_sweep_kernel<KT, 0><<<g.grid, g.warps * 32, sh, st>>>(                                             \
-            csf, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_a);  \
-        phase_end(ctx, ITR_PH_POST_FWD, st);                                                                          \
-        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));                                                                 \
         CK(cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht));  \
-        phase_begin(ctx, ITR_PH_POST_COMBINE, st);                                                                    \
-        for (int q = 0; q < n_slices; ++q) {                                                                          \
-            const int64_t nt = slice_tile[q + 1] - slice_tile[q];                                                     \
-            if (nt <= 0) continue;                                                                                    \
-            const unsigned gt = (unsigned)std::min<int64_t>((nt + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6); \
-            posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
-                                                                 slice_tile[q], slice_tile[q + 1], ctx->d_A, ctx->d_PI, \
-                                                                 ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K, ctx->d_post); \
-            ctx->launches += 1;                                                                                       \
-            if (post) {                                                                                               \
-                CK(cudaEventRecord(ecopy, st));                                                                       \
-                CK(cudaStreamWaitEvent(scopy, ecopy, 0));                                                             \
-                const size_t o = (size_t)slice_col[q] * K, len = (size_t)(slice_col[q + 1] - slice_col[q]) * K;       \
-                CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, scopy));  \
+        for (int gi = n_groups - 1; gi >= 0; --gi) {                                                                  \
+            const int first = (int)((int64_t)nb * gi / n_groups), last = (int)((int64_t)nb * (gi + 1) / n_groups);    \
+            if (last <= first) continue;                                                                              \
+            const bool whole = (n_groups == 1);                                                                       \
+            cudaStream_t sf = whole ? st : ctx->grp_streams[2 * gi], sb = whole ? ctx->stream2 : ctx->grp_streams[2 * gi + 1]; \
+            ChainSet cf = chain_set(ctx, 1, whole ? 3 : 24 + 2 * gi), cb = chain_set(ctx, 1, whole ? 1 : 25 + 2 * gi); \
+            cf.order += first; cf.n_blocks = last - first;                                                            \
+            cb.order += first; cb.n_blocks = last - first;                                                            \
+            const Geometry g = geometry(ctx, last - first, 12);                                                       \
+            const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);                                              \
+            if (!whole) {                                                                                             \
+                CK(cudaStreamWaitEvent(sf, ctx->ev_fork, 0));                                                         \
+                CK(cudaStreamWaitEvent(sb, ctx->ev_fork, 0));                                                         \
+            }                                                                                                         \
+            cudaMemsetAsync(cb.queue, 0, sizeof(unsigned int), sb);                                                   \
+            cudaMemsetAsync(cf.queue, 0, sizeof(unsigned int), sf);                                                   \
+            if (gi == 0) phase_begin(ctx, ITR_PH_POST_BWD, sb);                                                       \
+            checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, sb>>>(                                         \
+                cb, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
+            if (gi == 0) phase_end(ctx, ITR_PH_POST_BWD, sb);                                                         \
+            if (gi == 0) phase_begin(ctx, ITR_PH_POST_FWD, sf);                                                       \
+            checkpoint_sweep_kernel<KT, 0><<<g.grid, g.warps * 32, sh, sf>>>(                                         \
+                cf, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_a); \
+            if (gi == 0) phase_end(ctx, ITR_PH_POST_FWD, sf);                                                         \
+            ctx->launches += 2;                                                                                       \
+            CK(cudaEventRecord(whole ? ctx->ev_join : ctx->grp_events[2 * gi + 1], sb));                             \
+            CK(cudaStreamWaitEvent(sf, whole ? ctx->ev_join : ctx->grp_events[2 * gi + 1], 0));                       \
+        }                                                                                                             \
+        /* second loop: a download into pageable memory blocks the host, so every sweep is enqueued first */        \
+        for (int gi = n_groups - 1; gi >= 0; --gi) {                                                                  \
+            const int first = (int)((int64_t)nb * gi / n_groups), last = (int)((int64_t)nb * (gi + 1) / n_groups);    \
+            if (last <= first) continue;                                                                              \
+            const bool whole = (n_groups == 1);                                                                       \
+            cudaStream_t sf = whole ? st : ctx->grp_streams[2 * gi];                                                  \
+            if (whole) {                                                                                              \
+                phase_begin(ctx, ITR_PH_POST_COMBINE, st);                                                            \
+                const int64_t nt = ctx->n_tiles;                                                                      \
+                const unsigned gt = (unsigned)std::min<int64_t>((nt + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6); \
+                posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
+                                                                     0, nt, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a,  \
+                                                                     ctx->d_ck_b, K, ctx->d_post);                     \
+                ctx->launches += 1;                                                                                   \
+                phase_end(ctx, ITR_PH_POST_COMBINE, st);                                                              \
+                if (post) {                                                                                           \
+                    CK(cudaEventRecord(ecopy, st));                                                                   \
+                    CK(cudaStreamWaitEvent(scopy, ecopy, 0));                                                         \
+                    CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, scopy));        \
+                }                                                                                                     \
+            } else {                                                                                                  \
+                /* pass 2 and download block by block, in the group's forward stream */                              \
+                if (gi == 0) phase_begin(ctx, ITR_PH_POST_COMBINE, sf);                                               \
+                for (int q = last - 1; q >= first; --q) {                                                             \
+                    const int32_t blk = ctx->h_order[q];                                                              \
+                    const int64_t t0 = ctx->h_tile_off[blk], t1 = ctx->h_tile_off[blk + 1];                           \
+                    if (t1 <= t0) continue;                                                                           \
+                    const unsigned gt = (unsigned)std::min<int64_t>((t1 - t0 + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6); \
+                    posterior_tiles_kernel<KT><<<gt, wt * 32, sht, sf>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
+                                                                         t0, t1, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, \
+                                                                         ctx->d_ck_b, K, ctx->d_post);                 \
+                    ctx->launches += 1;                                                                               \
+                    CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));                                                 \
+                    CK(cudaStreamWaitEvent(scopy, ctx->grp_events[2 * gi], 0));                                       \
+                    const size_t o = (size_t)ctx->h_off[blk] * K, len = (size_t)(ctx->h_off[blk + 1] - ctx->h_off[blk]) * K; \
+                    CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, scopy)); \
+                }                                                                                                     \
+                if (gi == 0) phase_end(ctx, ITR_PH_POST_COMBINE, sf);                                                 \
             }                                                                                                         \
         }                                                                                                             \
-        phase_end(ctx, ITR_PH_POST_COMBINE, st);                                                                      \
     } while (0)
         switch ((K + 3) / 4) {
             case 1: POST2(4); break;
@@ -1033,14 +1067,13 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
             default: POST2(32); break;
         }
 #undef POST2
-        phase_end(ctx, ITR_PH_POST_TOTAL, st);
-        ctx->launches += 2;
         CK(cudaGetLastError());
         ctx->have_post = true;
         if (post) {                       // the posterior stream also waits for the downloads
             CK(cudaEventRecord(ecopy, scopy));
             CK(cudaStreamWaitEvent(st, ecopy, 0));
         }
+        phase_end(ctx, ITR_PH_POST_TOTAL, st);
         if (!ctx->async) CK(cudaStreamSynchronize(st));
         return ITR_OK;
     }

@@ -385,13 +385,16 @@ symbol_class_kernel(const double *__restrict__ Et, int K, int KP, int n_sets, do
 
 __global__ void __launch_bounds__(256)
 symbol_hist_kernel(const uint16_t *__restrict__ sym, int64_t n, unsigned long long *__restrict__ hist) {
-    __shared__ unsigned int h[NSYM];
-    for (int i = threadIdx.x; i < NSYM; i += blockDim.x) h[i] = 0;
+    // bin NSYM counts symbols outside 0..624 (the load is rejected if it is not zero)
+    __shared__ unsigned int h[NSYM + 1];
+    for (int i = threadIdx.x; i <= NSYM; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[sym[i]], 1u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned int v = sym[i];
+        atomicAdd(&h[v < (unsigned)NSYM ? v : (unsigned)NSYM], 1u);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < NSYM; i += blockDim.x)
+    for (int i = threadIdx.x; i <= NSYM; i += blockDim.x)
         if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
 }
 

@@ -275,3 +275,21 @@ def test_run_compressed_loglik_equals_plain_sweep(engine, monkeypatch):
     engine.set_model(a, b, pi)
     _, pb = engine.loglik(per_block=True)
     np.testing.assert_allclose(pb[0], hoc.loglik_blocks(a, ho.emission_table(b), pi, V_rand), rtol=LL_RTOL)
+
+
+def test_out_of_range_symbol_is_rejected_by_the_library(engine):
+    """list.index raises in the reference's maf_parser (read_data.py:113-115); through the
+    C ABI a symbol > 624 is caught by the device-side range check of itr_load_blocks."""
+    sym = np.zeros(5000, dtype=np.uint16)
+    sym[4321] = 625
+    off = np.array([0, 3000, 5000], dtype=np.int64)
+    with pytest.raises(ValueError, match="column 4321"):
+        engine.load_packed(sym, off)
+    with pytest.raises(Exception):
+        engine.loglik()                       # nothing is resident after a rejected load
+    sym[4321] = 624
+    engine.load_packed(sym, off)
+    m = golden("model_2_2_example.npz")
+    engine.set_model(m["a"], m["b"], m["pi"])
+    ref = hoc.loglik_blocks(m["a"], ho.emission_table(m["b"]), m["pi"], [sym[:3000].astype(np.int64), sym[3000:].astype(np.int64)])
+    np.testing.assert_allclose(engine.loglik(per_block=True)[1][0], ref, rtol=LL_RTOL)
