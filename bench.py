@@ -33,6 +33,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# read when the CUDA context is created (torch may create it first): see itrails_b200/__init__.py
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SEED0 = 20261018
 WORKLOADS = {

@@ -15,6 +15,13 @@ Everything numeric runs in hand-written CUDA behind a C ABI
 fallback: importing the package is cheap, but any compute call raises
 ``ItrailsCudaError`` if the library or a B200-class GPU is missing.
 """
+import os as _os
+
+# ~20 concurrent CUDA streams (recursions, posterior length groups, copies): more hardware
+# work queues than the default 8, or they alias and serialise.  Must be set before the CUDA
+# context exists; libitrails_b200.so sets it too when it is loaded first.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 __version__ = "0.1.0"
 
 from ._lib import ItrailsCudaError, ItrailsError  # noqa: F401

@@ -37,6 +37,8 @@ struct itr_ctx {
     // backward) so that independent recursions overlap on the device.
     cudaStream_t stream = nullptr, s_ll = nullptr, s_vit = nullptr, s_post = nullptr, stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ready = nullptr;
+    cudaEvent_t ev_post_compute = nullptr;   // kernels of a posterior that is being downloaded are done
+    bool post_download = false;
     bool async = false;
     double *pend_total = nullptr, *pend_per_block = nullptr;   // host outputs of a deferred itr_loglik
     bool pend_ll = false;
@@ -55,6 +57,10 @@ struct itr_ctx {
     size_t cap_sym = 0, cap_off = 0, cap_order = 0, cap_chunk_off = 0, cap_chunk_blk = 0;
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_order;
+    // ITR_POST_TRACE=1 (debug): per-block timeline of the posterior download, printed at the next sync
+    std::vector<cudaEvent_t> tr_k, tr_c;
+    std::vector<int32_t> tr_b;
+    cudaEvent_t tr_0 = nullptr;
     std::vector<int64_t> h_tile_off;
     std::vector<cudaStream_t> grp_streams;     // 2 per posterior group
     std::vector<cudaEvent_t> grp_events;       // 2 per posterior group
@@ -116,6 +122,17 @@ static int fail(itr_ctx *c, int code, const char *fmt, ...) {
     if (c) c->err = buf; else g_create_error = buf;
     return code;
 }
+
+// The recursions, the posterior length groups and the copy stream are ~20 concurrent CUDA
+// streams; with the default of 8 hardware work queues they alias and serialise behind
+// each other (measured: log-likelihood 7 -> 17 ms inside a step).  The variable is read
+// when the CUDA context is created, so it is set when the library is loaded; a value
+// chosen by the user wins.
+namespace {
+struct ConnectionsEnv {
+    ConnectionsEnv() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connections_env;
+}  // namespace
 
 #define CK(call)                                                                       \
     do {                                                                               \
@@ -196,6 +213,7 @@ extern "C" int itr_create(int device, itr_ctx **out) {
         if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_post_compute, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
         if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -244,6 +262,7 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_post_compute) cudaEventDestroy(ctx->ev_post_compute);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     for (cudaStream_t st : {ctx->s_ll, ctx->s_vit, ctx->s_post, ctx->stream2})
@@ -283,6 +302,34 @@ extern "C" int64_t itr_num_blocks(const itr_ctx *ctx) { return ctx ? ctx->n_bloc
 // Data or model are about to change: drain every recursion stream first.
 static int quiesce(itr_ctx *ctx);
 static int prepare_runs(itr_ctx *ctx, cudaStream_t st);
+
+static void dump_trace(itr_ctx *ctx) {
+    if (!ctx->tr_0) return;
+    cudaStreamSynchronize(ctx->s_post);
+    for (size_t i = 0; i < ctx->tr_b.size(); ++i) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->tr_0, ctx->tr_k[i]);
+        cudaEventElapsedTime(&b, ctx->tr_0, ctx->tr_c[i]);
+        fprintf(stderr, "post-trace block %d len %lld pass2_done %.3f copy_done %.3f\n", ctx->tr_b[i],
+                (long long)(ctx->h_off[ctx->tr_b[i] + 1] - ctx->h_off[ctx->tr_b[i]]), a, b);
+        cudaEventDestroy(ctx->tr_k[i]);
+        cudaEventDestroy(ctx->tr_c[i]);
+    }
+    for (int ph : {(int)ITR_PH_LOGLIK, (int)ITR_PH_VITERBI_FWD, (int)ITR_PH_POST_FWD, (int)ITR_PH_POST_TOTAL}) {
+        float a = -1, b = -1;
+        if (ctx->ev_valid[ph] && cudaEventSynchronize(ctx->ev1[ph]) == cudaSuccess) {
+            if (cudaEventElapsedTime(&a, ctx->tr_0, ctx->ev0[ph]) != cudaSuccess) a = -1;
+            if (cudaEventElapsedTime(&b, ctx->tr_0, ctx->ev1[ph]) != cudaSuccess) b = -1;
+        }
+        cudaGetLastError();
+        fprintf(stderr, "post-trace phase %d begin %.3f end %.3f\n", ph, a, b);
+    }
+    cudaEventDestroy(ctx->tr_0);
+    ctx->tr_0 = nullptr;
+    ctx->tr_k.clear();
+    ctx->tr_c.clear();
+    ctx->tr_b.clear();
+}
 
 static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off, int64_t n_blocks) {
     CK(cudaSetDevice(ctx->device));
@@ -539,6 +586,12 @@ static Geometry geometry(const itr_ctx *ctx, int64_t n_chains, int max_warps_per
     return {w, (int)std::max<int64_t>(1, std::min(want, cap))};
 }
 
+// Work-queue counters are zeroed by a one-thread kernel, not cudaMemsetAsync: a memset may
+// be executed by a copy engine, where it queues behind a posterior download in progress
+// (measured: the log-likelihood of a step started only after the 2 GB transfer, +5.7 ms).
+__global__ void zero_u32_kernel(unsigned int *p) { *p = 0u; }
+static inline void reset_queue(unsigned int *q, cudaStream_t st) { zero_u32_kernel<<<1, 1, 0, st>>>(q); }
+
 static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
     return ChainSet{ctx->d_sym, ctx->d_off, ctx->d_order, (int32_t)ctx->n_blocks, n_sets, ctx->d_queue + slot};
 }
@@ -589,7 +642,7 @@ static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alp
         cs.order += first;
         cs.n_blocks = count;
     }
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    reset_queue(cs.queue, st);
     if (K > 32 && K <= 96) {        // one CTA of ceil(K/32) warps per chain, columns of a in registers
         const int grid = (int)std::min<int64_t>((int64_t)n_sets * cs.n_blocks, (int64_t)ctx->prop.multiProcessorCount * 8);
         if (K <= 64) sweep_mw_kernel<2, 0, MODE><<<grid, 64, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha);
@@ -616,7 +669,7 @@ static void launch_backward(itr_ctx *ctx, cudaStream_t st, int slot = 1, int fir
         cs.order += first;
         cs.n_blocks = count;
     }
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    reset_queue(cs.queue, st);
     if (K > 32 && K <= 96) {
         const int grid = (int)std::min<int64_t>(cs.n_blocks, (int64_t)ctx->prop.multiProcessorCount * 8);
         if (K <= 64) sweep_mw_kernel<2, 1, 1><<<grid, 64, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, nullptr, ctx->d_beta);
@@ -667,7 +720,7 @@ static cudaError_t launch_combine(itr_ctx *ctx, cudaStream_t st) {
 static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const int K = ctx->K, KP = ctx->KP;
     const ChainSet cs = chain_set(ctx, 1, 2);
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    reset_queue(cs.queue, st);
     ctx->launches += 1;
     // Few chains: four warps per chain (latency); many chains: one warp per chain (throughput).
     const int sms = ctx->prop.multiProcessorCount;
@@ -746,7 +799,7 @@ static void launch_forward_runs(itr_ctx *ctx, double *d_ll, cudaStream_t st) {
     const ChainSet cs = chain_set(ctx, ctx->n_sets, 0);
     const Geometry g = geometry(ctx, (int64_t)ctx->n_sets * ctx->n_blocks, 12);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    cudaMemsetAsync(cs.queue, 0, sizeof(unsigned int), st);
+    reset_queue(cs.queue, st);
 #define RUN_K(KT)                                                                                        \
     forward_runs_kernel<KT><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P, \
                                                               ctx->d_sP, ctx->d_ebar, ctx->d_isrun, K, d_ll)
@@ -805,6 +858,7 @@ extern "C" int itr_sync(itr_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     for (cudaStream_t st : {ctx->stream, ctx->s_ll, ctx->s_vit, ctx->s_post, ctx->stream2}) CK(cudaStreamSynchronize(st));
     finish_loglik(ctx);
+    dump_trace(ctx);
     return ITR_OK;
 }
 
@@ -832,6 +886,9 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
         ctx->cap_hll = n;
     }
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    // (No wait for a posterior download here, unlike itr_viterbi: this sweep is one warp per
+    // block and does not crowd out the posterior's kernels — and measured, this stream's
+    // wait on ev_post_compute was only released when the whole download had finished.)
     const bool runs = ctx->K <= 32 && ctx->use_runs && ctx->runs_valid && !getenv("ITR_NO_RUNS");   // (variable: experiments, tests)
     phase_begin(ctx, ITR_PH_LOGLIK, st);
     if (runs) launch_forward_runs(ctx, ctx->d_ll, st);
@@ -884,6 +941,9 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
     CK(ensure(ctx->d_final, ctx->cap_final, (size_t)nb));
     double *t_la = ctx->d_tmp, *t_le = t_la + n_la, *t_om = t_le + n_le;
     CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    // A posterior on its way to the host is PCIe bound (2 GB); its kernels go first, so
+    // that the download starts early, and this recursion runs under the transfer.
+    if (ctx->post_download) CK(cudaStreamWaitEvent(st, ctx->ev_post_compute, 0));
     CK(cudaMemcpyAsync(t_la, log_a, n_la * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t_le, log_E, n_le * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t_om, omega0, n_om * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -973,8 +1033,9 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         // stream — the 2 GB PCIe transfer starts after the SHORTEST blocks' sweeps and
         // hides the long blocks' latency-bound sweeps.
         const int nb = (int)ctx->n_blocks;
-        const int n_groups = post ? std::min(8, std::max(1, nb / 2)) : 1;
-        while (post && (int)ctx->grp_streams.size() < 2 * 8 + 1) {
+        // (with hundreds of chains the sweeps fill the GPU by themselves: one group, one pass-2 launch)
+        const int n_groups = (getenv("ITR_POST_ONE_GROUP") || (!post && nb > 256)) ? 1 : std::min(8, std::max(1, nb / 2));
+        while ((int)ctx->grp_streams.size() < 2 * 8 + 1) {
             cudaStream_t s2 = nullptr;
             cudaEvent_t e2 = nullptr;
             CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -982,8 +1043,14 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
             CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
             ctx->grp_events.push_back(e2);
         }
-        cudaStream_t scopy = post ? ctx->grp_streams[16] : nullptr;
-        cudaEvent_t ecopy = post ? ctx->grp_events[16] : nullptr;
+        const bool trace = post && getenv("ITR_POST_TRACE");      // debug: per-block timeline on stderr
+        if (trace) {
+            dump_trace(ctx);
+            cudaEventCreate(&ctx->tr_0);
+            cudaEventRecord(ctx->tr_0, st);
+        }
+        cudaStream_t scopy = ctx->grp_streams[16];
+        cudaEvent_t ecopy = ctx->grp_events[16];
 #define POST2(KT)                                                                                                     \
     do {                                                                                                              \
         CK(cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht));  \
@@ -1001,8 +1068,8 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                 CK(cudaStreamWaitEvent(sf, ctx->ev_fork, 0));                                                         \
                 CK(cudaStreamWaitEvent(sb, ctx->ev_fork, 0));                                                         \
             }                                                                                                         \
-            cudaMemsetAsync(cb.queue, 0, sizeof(unsigned int), sb);                                                   \
-            cudaMemsetAsync(cf.queue, 0, sizeof(unsigned int), sf);                                                   \
+            reset_queue(cb.queue, sb);                                                   \
+            reset_queue(cf.queue, sf);                                                   \
             if (gi == 0) phase_begin(ctx, ITR_PH_POST_BWD, sb);                                                       \
             checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, sb>>>(                                         \
                 cb, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
@@ -1047,12 +1114,23 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                                                                          t0, t1, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, \
                                                                          ctx->d_ck_b, K, ctx->d_post);                 \
                     ctx->launches += 1;                                                                               \
+                    if (!post) continue;                                                                              \
                     CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));                                                 \
+                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sf); ctx->tr_k.push_back(e); } \
                     CK(cudaStreamWaitEvent(scopy, ctx->grp_events[2 * gi], 0));                                       \
                     const size_t o = (size_t)ctx->h_off[blk] * K, len = (size_t)(ctx->h_off[blk + 1] - ctx->h_off[blk]) * K; \
                     CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, scopy)); \
+                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, scopy); ctx->tr_c.push_back(e); ctx->tr_b.push_back(blk); } \
                 }                                                                                                     \
                 if (gi == 0) phase_end(ctx, ITR_PH_POST_COMBINE, sf);                                                 \
+                if (post) {                        /* stream2 collects "kernels done" of every group */              \
+                    CK(cudaEventRecord(ctx->grp_events[2 * gi + 1], sf));                                             \
+                    CK(cudaStreamWaitEvent(ctx->stream2, ctx->grp_events[2 * gi + 1], 0));                            \
+                }                                                                                                     \
+                if (!post) {                       /* join the group into the copy stream's place: st waits below */ \
+                    CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));                                                 \
+                    CK(cudaStreamWaitEvent(st, ctx->grp_events[2 * gi], 0));                                          \
+                }                                                                                                     \
             }                                                                                                         \
         }                                                                                                             \
     } while (0)
@@ -1069,11 +1147,17 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
 #undef POST2
         CK(cudaGetLastError());
         ctx->have_post = true;
+        ctx->post_download = false;
+        if (post && n_groups > 1) {
+            CK(cudaEventRecord(ctx->ev_post_compute, ctx->stream2));
+            ctx->post_download = true;
+        }
         if (post) {                       // the posterior stream also waits for the downloads
             CK(cudaEventRecord(ecopy, scopy));
             CK(cudaStreamWaitEvent(st, ecopy, 0));
         }
         phase_end(ctx, ITR_PH_POST_TOTAL, st);
+        if (trace && !ctx->async) dump_trace(ctx);
         if (!ctx->async) CK(cudaStreamSynchronize(st));
         return ITR_OK;
     }
