@@ -727,7 +727,31 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "spec", "4warp", "1warp"
     // (speculation pays when backpointers are stable, i.e. on alignments dominated by a few
     // symbols — the same test that enables run compression; else every window mispredicts)
-    const bool want_spec = vmode ? !strcmp(vmode, "spec") : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms / 2);
+    const bool want_spec = vmode ? (!strcmp(vmode, "spec") || !strcmp(vmode, "stream")) : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms / 2);
+    const bool want_stream = vmode ? !strcmp(vmode, "stream") : false;
+    if (K <= 32 && want_spec && want_stream && ctx->max_T < 0x7fffffff) {
+        // decoupled speculate-and-verify sweep: runner, feeder and 14 verifiers per chain
+        const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);
+        const size_t shs = (size_t)(NSYM * 32 + 2 * STR_R * 32) * sizeof(double) + (size_t)STR_R * 32;
+#define VSTR(KT)                                                                                               \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(viterbi_stream_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shs); \
+        viterbi_stream_kernel<KT><<<grid, 32 * STR_NW, shs, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K,    \
+                                                                  ctx->d_bp, ctx->d_final);                    \
+    } while (0)
+        switch ((K + 3) / 4) {
+            case 1: VSTR(4); break;
+            case 2: VSTR(8); break;
+            case 3: VSTR(12); break;
+            case 4: VSTR(16); break;
+            case 5: VSTR(20); break;
+            case 6: VSTR(24); break;
+            case 7: VSTR(28); break;
+            default: VSTR(32); break;
+        }
+#undef VSTR
+        return;
+    }
     if (K <= 32 && want_spec && !getenv("ITR_VITERBI_1WARP")) {
         // speculate-and-verify sweep: one CTA of 16 warps per chain
         const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);

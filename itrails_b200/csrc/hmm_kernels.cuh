@@ -1683,6 +1683,241 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Viterbi forward sweep, speculation and verification DECOUPLED (K <= 32, few chains).
+//
+// Same idea and same exactness argument as viterbi_spec_kernel, but the runner never waits
+// for a window to be verified: it streams columns into a ring of STR_R slots and only
+// stops when a verifier raises a mismatch.  Roles in a CTA of 16 warps:
+//   warp 0       runner   omega_t[j] = (max over the candidate pair (lo, hi) of omega_{t-1}[p]
+//                         + log a[p][j]) + log e_t[j]; publishes run_t
+//   warp 15      feeder   stages the log-emission row of every upcoming column in the ring
+//                         (the runner's and the verifiers' lookups become plain indexed loads)
+//   warps 1..14  verifiers, column u belongs to warp 1 + (u mod 14): full exact scan from the
+//                         speculative omega_{u-1}; equal pointers -> commit the backpointer
+//                         row; else store the verified (arg, omega) and lower fail_t to u
+// Epochs: when fail_t is set (a mismatch, or the virtual one at column T that ends the block)
+// every verifier still finishes its columns below fail_t, then all warps meet at a barrier;
+// by then every column < fail_t is verified (fail_t only decreases), column fail_t takes the
+// verifier's result, the runner's candidate pair is updated and everyone resumes at
+// fail_t + 1.  A column is always re-verified by the same warp, so a backpointer row written
+// from a speculation that was later rolled back is overwritten in program order.
+// Ring slots are reused 64 columns later; the runner and the feeder poll the verifiers'
+// progress (every 4 columns, consumed 4 columns later) and wait if they would overrun it.
+// ---------------------------------------------------------------------------------
+constexpr int STR_R = 64, STR_NV = 14, STR_NW = 16;
+constexpr int STR_NONE = 0x7fffffff;
+
+template <int KT>
+__global__ void __launch_bounds__(32 * STR_NW)
+viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
+                      const double *__restrict__ OM0, int K,
+                      uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
+    constexpr int KP = 32, R = STR_R, NV = STR_NV;
+    __shared__ double las[KP][KP];                      // log a, for the runner's pointer lookups
+    __shared__ __align__(16) double vrom[STR_NW][KP];   // verified omega of a mismatching column, per verifier
+    __shared__ int varg[STR_NW][KP];                    // its verified first arg-maxima
+    __shared__ volatile int vfail[STR_NW];              // the column it belongs to (STR_NONE: none)
+    __shared__ volatile int ver_next[STR_NW];           // next column each verifier will look at
+    __shared__ volatile int run_t, feed_t, fail_t;      // last column produced / staged (exclusive) / first bad column
+    __shared__ int chain_s;
+    extern __shared__ __align__(16) double dyn[];
+    double *les = dyn;                                                   // [NSYM][KP] log-emission table
+    double (*ring_om)[KP] = reinterpret_cast<double (*)[KP]>(dyn + NSYM * KP);          // omega after column t, slot t % R
+    double (*ring_ew)[KP] = reinterpret_cast<double (*)[KP]>(dyn + NSYM * KP + R * KP); // log e row of column t
+    uint8_t (*ring_ptr)[KP] = reinterpret_cast<uint8_t (*)[KP]>(dyn + NSYM * KP + 2 * R * KP);  // the runner's choice
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_chains = cs.n_blocks;
+    const int K4 = (K + 3) & ~3;
+    for (int e = threadIdx.x; e < NSYM * KP; e += blockDim.x) les[e] = __ldg(LEt + e);
+    Cols<KT, 1, true> lacol;                            // column `lane` of log a (verifiers)
+    if (warp >= 1 && warp <= NV) lacol.load(LA, KP, lane);
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) las[e / KP][e % KP] = __ldg(LA + e);
+    __syncthreads();
+
+    for (;;) {
+        if (threadIdx.x == 0) chain_s = (int)atomicAdd(cs.queue, 1u);
+        __syncthreads();
+        const int c = chain_s;
+        __syncthreads();
+        if (c >= n_chains) break;
+        const int blk = cs.order[c];
+        const int64_t beg = cs.off[blk];
+        const int T = (int)(cs.off[blk + 1] - beg);     // (block lengths fit in 31 bits; checked by the host)
+        const uint16_t *symp = cs.sym + beg;
+        uint8_t *bpl = bp + (size_t)beg * KP + lane;
+
+        // runner state: the two most recent predecessors of state `lane`, sorted by index
+        int lo = lane, hi = lane;
+        double la_lo = las[lane][lane], la_hi = la_lo;
+        int t_run = 1;                                  // runner: next column to produce
+        int t_feed = 1;                                 // feeder: next column to stage
+        int u_ver = (warp >= 1 && warp <= NV) ? ((1 % NV == warp % NV) ? 1 : 1 + ((warp % NV) - (1 % NV) + NV) % NV) : STR_NONE;
+        if (warp == 0) {
+            ring_om[0][lane] = __ldg(OM0 + (size_t)blk * KP + lane);
+            if (lane == 0) { run_t = 0; feed_t = 1; fail_t = STR_NONE; }
+        }
+        if (lane == 0) { vfail[warp] = STR_NONE; ver_next[warp] = (warp >= 1 && warp <= NV) ? u_ver : STR_NONE; }
+        __syncthreads();
+
+        for (;;) {                                      // epochs between roll-backs
+            if (warp == 0) {
+                // ---------------- runner ----------------
+                int p_fail = STR_NONE, p_feed = feed_t, p_min = 1;
+                {
+                    const int mv = ver_next[1 + lane % NV];
+                    p_min = __reduce_min_sync(FULL, mv);
+                }
+                double xl = ring_om[(t_run - 1) & (R - 1)][lo], xh = ring_om[(t_run - 1) & (R - 1)][hi];
+                bool stop = false;
+                while (!stop) {
+                    if (t_run >= T) { if (lane == 0) atomicMin((int *)&fail_t, T); break; }
+                    // probes issued 4 columns ago: is it safe to produce columns t_run .. t_run+3?
+                    if (p_fail != STR_NONE) break;
+                    while (p_feed < min(t_run + 5, T) || p_min + (R - 1) <= t_run + 3) {
+                        __nanosleep(64);
+                        if (fail_t != STR_NONE) { stop = true; break; }
+                        p_feed = feed_t;
+                        const int mv = ver_next[1 + lane % NV];
+                        p_min = __reduce_min_sync(FULL, mv);
+                    }
+                    if (stop) break;
+                    p_fail = fail_t;
+                    const int q_feed = feed_t;
+                    const int q_mv = ver_next[1 + lane % NV];
+                    double ew = ring_ew[t_run & (R - 1)][lane];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (t_run < T) {
+                            const int slot = t_run & (R - 1);
+                            const double ew_n = ring_ew[(t_run + 1) & (R - 1)][lane];   // (staged: p_feed >= t_run + 5)
+                            const double s_l = __dadd_rn(xl, la_lo), s_h = __dadd_rn(xh, la_hi);
+                            const bool take = s_h > s_l;                             // (the verifier has the last word)
+                            const double M = __dadd_rn(take ? s_h : s_l, ew);
+                            ring_om[slot][lane] = M;
+                            ring_ptr[slot][lane] = (uint8_t)(take ? hi : lo);
+                            __syncwarp();
+                            xl = ring_om[slot][lo];
+                            xh = ring_om[slot][hi];
+                            ew = ew_n;
+                            ++t_run;
+                        }
+                    }
+                    __threadfence_block();
+                    if (lane == 0) run_t = t_run - 1;
+                    p_feed = q_feed;
+                    p_min = __reduce_min_sync(FULL, q_mv);
+                }
+            } else if (warp == STR_NW - 1) {
+                // ---------------- feeder ----------------
+                for (;;) {
+                    if (fail_t != STR_NONE) break;
+                    if (t_feed >= T) { __nanosleep(256); continue; }
+                    // slot reuse: column t_feed + 31 - R must be verified
+                    const int mv = ver_next[1 + lane % NV];
+                    const int vmin = __reduce_min_sync(FULL, mv);
+                    const int n = min(min(32, T - t_feed), vmin + R - 1 - t_feed);
+                    if (n <= 0) { __nanosleep(128); continue; }
+                    const int mysym = (int)__ldg(symp + t_feed + lane);     // (64 columns of slack behind the last block)
+                    for (int i = 0; i < n; ++i) {
+                        const int sy = __shfl_sync(FULL, mysym, i);
+                        ring_ew[(t_feed + i) & (R - 1)][lane] = les[sy * KP + lane];
+                    }
+                    t_feed += n;
+                    __threadfence_block();
+                    if (lane == 0) feed_t = t_feed;
+                }
+            } else {
+                // ---------------- verifiers ----------------
+                for (;;) {
+                    const int u = u_ver;
+                    bool go = true;
+                    while (run_t < u) {
+                        if (fail_t <= u) { go = false; break; }
+                        __nanosleep(32);
+                    }
+                    if (!go || fail_t <= u) break;
+                    __threadfence_block();
+                    __syncwarp();
+                    const int myp = ring_ptr[u & (R - 1)][lane];
+                    const double le = ring_ew[u & (R - 1)][lane];
+                    const double *xin = &ring_om[(u - 1) & (R - 1)][0];
+                    const double2 *x2 = reinterpret_cast<const double2 *>(xin);
+                    double sv[KT];
+                    int ix[KT];
+#pragma unroll
+                    for (int q = 0; q < KT; q += 2) {
+                        const double2 pq = x2[q / 2];
+                        sv[q] = __dadd_rn(pq.x, lacol.get(0, q));
+                        sv[q + 1] = __dadd_rn(pq.y, lacol.get(0, q + 1));
+                        ix[q] = q;
+                        ix[q + 1] = q + 1;
+                    }
+                    tournament<KT>(sv, ix);
+                    double M = __dadd_rn(sv[0], le);
+                    int arg = ix[0];
+                    if (__any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(sv[0], le, M))) {
+                        const ScanResult r = viterbi_exact_scan(xin, LA + lane, KP, K4, le);
+                        M = r.best;
+                        arg = r.arg;
+                    }
+                    if (__any_sync(FULL, (lane < K) & (arg != myp))) {
+                        vrom[warp][lane] = M;
+                        varg[warp][lane] = arg;
+                        __threadfence_block();
+                        if (lane == 0) { vfail[warp] = u; atomicMin((int *)&fail_t, u); }
+                        break;
+                    }
+                    bpl[(size_t)u * KP] = (uint8_t)myp;
+                    u_ver = u + NV;
+                    if (lane == 0) ver_next[warp] = u + NV;
+                }
+            }
+            __syncthreads();                            // everyone stopped; every column < fail_t is verified
+            const int f = fail_t;
+            __syncthreads();
+            if (f >= T) break;                          // the virtual mismatch at column T: block done
+            if (warp == 0) {
+                const int vf = vfail[lane & (STR_NW - 1)];
+                const unsigned who = __ballot_sync(FULL, lane < STR_NW && vf == f);
+                const int v = __ffs(who) - 1;
+                const int np2 = varg[v][lane], chosen = ring_ptr[f & (R - 1)][lane];
+                // new candidate pair: the verified predecessor and the most recent other one
+                const int other = (chosen != np2) ? chosen : (lo != np2) ? lo : hi;
+                lo = min(np2, other);
+                hi = max(np2, other);
+                la_lo = las[lo][lane];
+                la_hi = las[hi][lane];
+                bpl[(size_t)f * KP] = (uint8_t)np2;
+                ring_om[f & (R - 1)][lane] = vrom[v][lane];
+                t_run = f + 1;
+                if (lane == 0) { run_t = f; fail_t = STR_NONE; }
+            } else if (warp <= NV) {
+                const int r0 = (f + 1) % NV;
+                u_ver = f + 1 + ((warp % NV) - r0 + NV) % NV;
+                if (lane == 0) { vfail[warp] = STR_NONE; ver_next[warp] = u_ver; }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            // first argmax of omega_{T-1}
+            const double om = ring_om[(T - 1) & (R - 1)][lane];
+            double best = (lane < K) ? om : -CUDART_INF;
+            int bidx = (lane < K) ? lane : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int oi = __shfl_xor_sync(FULL, bidx, o);
+                if (oi != 0x7fffffff && (bidx == 0x7fffffff || ob > best || (ob == best && oi < bidx))) {
+                    best = ob; bidx = oi;
+                }
+            }
+            if (lane == 0) final_state[blk] = bidx;
+        }
+        __syncthreads();
+    }
+}
+
 // Parallel traceback, step 1: one warp per VCHUNK-column chunk.  The chunk's
 // backpointer rows are staged in shared memory with coalesced 16-byte loads; lane j
 // then follows them from state j at the chunk's last column to the state at the last
