@@ -724,11 +724,11 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     ctx->launches += 1;
     // Few chains: four warps per chain (latency); many chains: one warp per chain (throughput).
     const int sms = ctx->prop.multiProcessorCount;
-    const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "spec", "4warp", "1warp"
+    const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "stream", "spec", "4warp", "1warp"
     // (speculation pays when backpointers are stable, i.e. on alignments dominated by a few
     // symbols — the same test that enables run compression; else every window mispredicts)
     const bool want_spec = vmode ? (!strcmp(vmode, "spec") || !strcmp(vmode, "stream")) : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms / 2);
-    const bool want_stream = vmode ? !strcmp(vmode, "stream") : false;
+    const bool want_stream = vmode ? !strcmp(vmode, "stream") : true;      // ("spec": the windowed predecessor)
     if (K <= 32 && want_spec && want_stream && ctx->max_T < 0x7fffffff) {
         // decoupled speculate-and-verify sweep: runner, feeder and 14 verifiers per chain
         const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);

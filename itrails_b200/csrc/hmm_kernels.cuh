@@ -1693,7 +1693,8 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
 //                         + log a[p][j]) + log e_t[j]; publishes run_t
 //   warp 15      feeder   stages the log-emission row of every upcoming column in the ring
 //                         (the runner's and the verifiers' lookups become plain indexed loads)
-//   warps 1..14  verifiers, column u belongs to warp 1 + (u mod 14): full exact scan from the
+//   other warps  verifiers (11: warps 4, 8, 12 idle so that the runner owns its scheduler), column u
+//                         belongs to verifier u mod 11: full exact scan from the
 //                         speculative omega_{u-1}; equal pointers -> commit the backpointer
 //                         row; else store the verified (arg, omega) and lower fail_t to u
 // Epochs: when fail_t is set (a mismatch, or the virtual one at column T that ends the block)
@@ -1705,8 +1706,21 @@ viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__
 // Ring slots are reused 64 columns later; the runner and the feeder poll the verifiers'
 // progress (every 4 columns, consumed 4 columns later) and wait if they would overrun it.
 // ---------------------------------------------------------------------------------
-constexpr int STR_R = 64, STR_NV = 14, STR_NW = 16;
+#ifndef ITR_STR_ISOLATE
+#define ITR_STR_ISOLATE 1
+#endif
+// ISOLATE: warps 4, 8, 12 stay idle so that the runner has its scheduler (and its FP64
+// pipe) to itself; 11 verifiers on the other three schedulers still verify ~2x faster
+// than the runner produces.
+constexpr int STR_R = 64, STR_NW = 16, STR_NV = ITR_STR_ISOLATE ? 11 : 14;
+#ifndef ITR_STR_G
+#define ITR_STR_G 8
+#endif
+constexpr int STR_G = ITR_STR_G;                 // columns the runner produces between two looks at the other warps
 constexpr int STR_NONE = 0x7fffffff;
+#ifndef ITR_STR_SLEEP
+#define ITR_STR_SLEEP 200
+#endif
 
 template <int KT>
 __global__ void __launch_bounds__(32 * STR_NW)
@@ -1731,7 +1745,10 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
     const int K4 = (K + 3) & ~3;
     for (int e = threadIdx.x; e < NSYM * KP; e += blockDim.x) les[e] = __ldg(LEt + e);
     Cols<KT, 1, true> lacol;                            // column `lane` of log a (verifiers)
-    if (warp >= 1 && warp <= NV) lacol.load(LA, KP, lane);
+    // verifier index of this warp (-1: runner, feeder or idle)
+    const int vi = (warp == 0 || warp == STR_NW - 1) ? -1
+                   : ITR_STR_ISOLATE ? ((warp & 3) ? warp - 1 - (warp >> 2) : -1) : warp - 1;
+    if (vi >= 0) lacol.load(LA, KP, lane);
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) las[e / KP][e % KP] = __ldg(LA + e);
     __syncthreads();
 
@@ -1752,61 +1769,77 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
         double la_lo = las[lane][lane], la_hi = la_lo;
         int t_run = 1;                                  // runner: next column to produce
         int t_feed = 1;                                 // feeder: next column to stage
-        int u_ver = (warp >= 1 && warp <= NV) ? ((1 % NV == warp % NV) ? 1 : 1 + ((warp % NV) - (1 % NV) + NV) % NV) : STR_NONE;
+        int u_ver = (vi >= 0) ? 1 + (vi - 1 + NV) % NV : STR_NONE;      // column u belongs to verifier u % NV
         if (warp == 0) {
             ring_om[0][lane] = __ldg(OM0 + (size_t)blk * KP + lane);
             if (lane == 0) { run_t = 0; feed_t = 1; fail_t = STR_NONE; }
         }
-        if (lane == 0) { vfail[warp] = STR_NONE; ver_next[warp] = (warp >= 1 && warp <= NV) ? u_ver : STR_NONE; }
+        if (lane == 0 && vi >= 0) { vfail[vi] = STR_NONE; ver_next[vi] = u_ver; }
         __syncthreads();
 
         for (;;) {                                      // epochs between roll-backs
             if (warp == 0) {
                 // ---------------- runner ----------------
-                int p_fail = STR_NONE, p_feed = feed_t, p_min = 1;
+                // Probes of the other warps' progress are issued at the top of a group of
+                // STR_G columns and consumed at the top of the next one (they only ever lag,
+                // which is conservative), so that their latency stays off the column chain.
+                constexpr int G = STR_G;
+                int p_fail = STR_NONE, p_feed = feed_t, p_min;
                 {
-                    const int mv = ver_next[1 + lane % NV];
+                    const int mv = ver_next[lane % NV];
                     p_min = __reduce_min_sync(FULL, mv);
                 }
                 double xl = ring_om[(t_run - 1) & (R - 1)][lo], xh = ring_om[(t_run - 1) & (R - 1)][hi];
-                bool stop = false;
+                double ew = 0.0;
+                bool have_ew = false, stop = false;
                 while (!stop) {
                     if (t_run >= T) { if (lane == 0) atomicMin((int *)&fail_t, T); break; }
-                    // probes issued 4 columns ago: is it safe to produce columns t_run .. t_run+3?
                     if (p_fail != STR_NONE) break;
-                    while (p_feed < min(t_run + 5, T) || p_min + (R - 1) <= t_run + 3) {
+                    // safe to produce columns t_run .. t_run+G-1 (and to read the emission row of t_run+G)?
+                    while (p_feed < min(t_run + G + 1, T) || p_min + (R - 1) <= t_run + G - 1) {
                         __nanosleep(64);
                         if (fail_t != STR_NONE) { stop = true; break; }
                         p_feed = feed_t;
-                        const int mv = ver_next[1 + lane % NV];
+                        const int mv = ver_next[lane % NV];
                         p_min = __reduce_min_sync(FULL, mv);
                     }
                     if (stop) break;
-                    p_fail = fail_t;
-                    const int q_feed = feed_t;
-                    const int q_mv = ver_next[1 + lane % NV];
-                    double ew = ring_ew[t_run & (R - 1)][lane];
+                    if (!have_ew) { ew = ring_ew[t_run & (R - 1)][lane]; have_ew = true; }
+                    const int q_fail = fail_t, q_feed = feed_t, q_mv = ver_next[lane % NV];
+                    int q_min = 0;
+                    // one column: two candidate sums, the better one plus the emission, exchange through the ring
+#define ITR_STR_COLUMN()                                                                                  \
+    do {                                                                                                  \
+        const int slot = t_run & (R - 1);                                                                 \
+        const double s_l = __dadd_rn(xl, la_lo), s_h = __dadd_rn(xh, la_hi);                              \
+        const bool take = s_h > s_l;                         /* (the verifier has the last word) */       \
+        const double M = __dadd_rn(take ? s_h : s_l, ew);                                                 \
+        ring_om[slot][lane] = M;                                                                          \
+        __syncwarp();                                                                                     \
+        xl = ring_om[slot][lo];                                                                           \
+        xh = ring_om[slot][hi];                                                                           \
+        ew = ring_ew[(t_run + 1) & (R - 1)][lane];           /* (staged: p_feed > t_run + G) */           \
+        ring_ptr[slot][lane] = (uint8_t)(take ? hi : lo);                                                 \
+        ++t_run;                                                                                          \
+    } while (0)
+                    if (t_run + G <= T) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (t_run < T) {
-                            const int slot = t_run & (R - 1);
-                            const double ew_n = ring_ew[(t_run + 1) & (R - 1)][lane];   // (staged: p_feed >= t_run + 5)
-                            const double s_l = __dadd_rn(xl, la_lo), s_h = __dadd_rn(xh, la_hi);
-                            const bool take = s_h > s_l;                             // (the verifier has the last word)
-                            const double M = __dadd_rn(take ? s_h : s_l, ew);
-                            ring_om[slot][lane] = M;
-                            ring_ptr[slot][lane] = (uint8_t)(take ? hi : lo);
-                            __syncwarp();
-                            xl = ring_om[slot][lo];
-                            xh = ring_om[slot][hi];
-                            ew = ew_n;
-                            ++t_run;
+                        for (int i = 0; i < G; ++i) {
+                            ITR_STR_COLUMN();
+                            if (i == 1) q_min = __reduce_min_sync(FULL, q_mv);   // (its operand has landed by now)
                         }
+                    } else {
+                        q_min = __reduce_min_sync(FULL, q_mv);
+                        while (t_run < T) ITR_STR_COLUMN();
                     }
+#undef ITR_STR_COLUMN
+#ifndef ITR_STR_NOFENCE
                     __threadfence_block();
+#endif
                     if (lane == 0) run_t = t_run - 1;
+                    p_fail = q_fail;
                     p_feed = q_feed;
-                    p_min = __reduce_min_sync(FULL, q_mv);
+                    p_min = q_min;
                 }
             } else if (warp == STR_NW - 1) {
                 // ---------------- feeder ----------------
@@ -1814,7 +1847,7 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                     if (fail_t != STR_NONE) break;
                     if (t_feed >= T) { __nanosleep(256); continue; }
                     // slot reuse: column t_feed + 31 - R must be verified
-                    const int mv = ver_next[1 + lane % NV];
+                    const int mv = ver_next[lane % NV];
                     const int vmin = __reduce_min_sync(FULL, mv);
                     const int n = min(min(32, T - t_feed), vmin + R - 1 - t_feed);
                     if (n <= 0) { __nanosleep(128); continue; }
@@ -1827,18 +1860,23 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                     __threadfence_block();
                     if (lane == 0) feed_t = t_feed;
                 }
-            } else {
+            } else if (vi >= 0) {
                 // ---------------- verifiers ----------------
                 for (;;) {
                     const int u = u_ver;
                     bool go = true;
                     while (run_t < u) {
                         if (fail_t <= u) { go = false; break; }
-                        __nanosleep(32);
+                        __nanosleep(ITR_STR_SLEEP);
                     }
                     if (!go || fail_t <= u) break;
                     __threadfence_block();
                     __syncwarp();
+#ifdef ITR_STR_ABL_NOVERIFY   /* ablation: accept every column unverified (results are wrong) */
+                    u_ver = u + NV;
+                    if (lane == 0) ver_next[vi] = u + NV;
+                    continue;
+#endif
                     const int myp = ring_ptr[u & (R - 1)][lane];
                     const double le = ring_ew[u & (R - 1)][lane];
                     const double *xin = &ring_om[(u - 1) & (R - 1)][0];
@@ -1862,15 +1900,15 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                         arg = r.arg;
                     }
                     if (__any_sync(FULL, (lane < K) & (arg != myp))) {
-                        vrom[warp][lane] = M;
-                        varg[warp][lane] = arg;
+                        vrom[vi][lane] = M;
+                        varg[vi][lane] = arg;
                         __threadfence_block();
-                        if (lane == 0) { vfail[warp] = u; atomicMin((int *)&fail_t, u); }
+                        if (lane == 0) { vfail[vi] = u; atomicMin((int *)&fail_t, u); }
                         break;
                     }
                     bpl[(size_t)u * KP] = (uint8_t)myp;
                     u_ver = u + NV;
-                    if (lane == 0) ver_next[warp] = u + NV;
+                    if (lane == 0) ver_next[vi] = u + NV;
                 }
             }
             __syncthreads();                            // everyone stopped; every column < fail_t is verified
@@ -1879,7 +1917,7 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
             if (f >= T) break;                          // the virtual mismatch at column T: block done
             if (warp == 0) {
                 const int vf = vfail[lane & (STR_NW - 1)];
-                const unsigned who = __ballot_sync(FULL, lane < STR_NW && vf == f);
+                const unsigned who = __ballot_sync(FULL, lane < NV && vf == f);
                 const int v = __ffs(who) - 1;
                 const int np2 = varg[v][lane], chosen = ring_ptr[f & (R - 1)][lane];
                 // new candidate pair: the verified predecessor and the most recent other one
@@ -1892,10 +1930,9 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                 ring_om[f & (R - 1)][lane] = vrom[v][lane];
                 t_run = f + 1;
                 if (lane == 0) { run_t = f; fail_t = STR_NONE; }
-            } else if (warp <= NV) {
-                const int r0 = (f + 1) % NV;
-                u_ver = f + 1 + ((warp % NV) - r0 + NV) % NV;
-                if (lane == 0) { vfail[warp] = STR_NONE; ver_next[warp] = u_ver; }
+            } else if (vi >= 0) {
+                u_ver = f + 1 + (vi - (f + 1) % NV + NV) % NV;
+                if (lane == 0) { vfail[vi] = STR_NONE; ver_next[vi] = u_ver; }
             }
             __syncthreads();
         }

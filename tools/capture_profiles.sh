@@ -9,9 +9,12 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.jso
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > /dev/null 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+# per step the bench launches: 3 expm kernels (model build), the Viterbi sweep, 16 checkpoint sweeps (8 length
+# groups x 2 directions), 100 per-block pass-2 kernels, the log-likelihood sweep.  Skip the 3 warm-up steps.
 ncu --set full --clock-control none --import-source on \
-    --kernel-name regex:'viterbi_spec_kernel|checkpoint_sweep_kernel|posterior_tiles_kernel|forward_runs_kernel|expm_kernel' \
-    --launch-skip 12 --launch-count 14 -f -o gpurun_out/prof_final $CMD > gpurun_out/ncu_full.log 2>&1
-ncu -i gpurun_out/prof_final.ncu-rep --page raw --csv > gpurun_out/ncu_final_raw.csv 2>/dev/null
-ncu -i gpurun_out/prof_final.ncu-rep --page source --csv --kernel-name regex:viterbi_spec_kernel > gpurun_out/ncu_final_source_viterbi.csv 2>/dev/null
+    --kernel-name regex:'viterbi_s.*_kernel|forward_runs_kernel|expm_kernel' \
+    --launch-skip 15 --launch-count 5 -f -o gpurun_out/prof_final_a $CMD > gpurun_out/ncu_full_a.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    --kernel-name regex:'checkpoint_sweep_kernel|posterior_tiles_kernel' \
+    --launch-skip 348 --launch-count 116 -f -o gpurun_out/prof_final_b $CMD > gpurun_out/ncu_full_b.log 2>&1
 ls -la gpurun_out | tail -12
