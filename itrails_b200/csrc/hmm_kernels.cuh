@@ -1880,6 +1880,10 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                     const int myp = ring_ptr[u & (R - 1)][lane];
                     const double le = ring_ew[u & (R - 1)][lane];
                     const double *xin = &ring_om[(u - 1) & (R - 1)][0];
+#ifdef ITR_STR_DEBUG
+                    if (lane == 0 && (u < 1 || u >= T || run_t < u))
+                        printf("STR-DEBUG blk %d verifier %d: column %d outside [1, %d) or ahead of run_t %d\n", blk, vi, u, T, run_t);
+#endif
                     const double2 *x2 = reinterpret_cast<const double2 *>(xin);
                     double sv[KT];
                     int ix[KT];
@@ -1913,13 +1917,26 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
             }
             __syncthreads();                            // everyone stopped; every column < fail_t is verified
             const int f = fail_t;
+            // Warp 0 picks up the verified result of column f HERE, between the two barriers,
+            // while nobody writes: after the second barrier the verifiers reset their slots
+            // concurrently with the repair (reading vfail there was a race that only showed
+            // under a profiler's timing).
+            int np2 = 0, chosen = 0;
+            double fix_om = 0.0;
+            if (warp == 0 && f < T) {
+                const int vf = vfail[lane & (STR_NW - 1)];
+                const unsigned who = __ballot_sync(FULL, lane < NV && vf == f);
+                const int v = who ? __ffs(who) - 1 : 0;
+#ifdef ITR_STR_DEBUG
+                if (who == 0 && lane == 0) printf("STR-DEBUG blk %d T %d: fail_t %d but no verifier owns it\n", blk, T, f);
+#endif
+                np2 = varg[v][lane];
+                fix_om = vrom[v][lane];
+                chosen = ring_ptr[f & (R - 1)][lane];
+            }
             __syncthreads();
             if (f >= T) break;                          // the virtual mismatch at column T: block done
             if (warp == 0) {
-                const int vf = vfail[lane & (STR_NW - 1)];
-                const unsigned who = __ballot_sync(FULL, lane < NV && vf == f);
-                const int v = __ffs(who) - 1;
-                const int np2 = varg[v][lane], chosen = ring_ptr[f & (R - 1)][lane];
                 // new candidate pair: the verified predecessor and the most recent other one
                 const int other = (chosen != np2) ? chosen : (lo != np2) ? lo : hi;
                 lo = min(np2, other);
@@ -1927,7 +1944,7 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                 la_lo = las[lo][lane];
                 la_hi = las[hi][lane];
                 bpl[(size_t)f * KP] = (uint8_t)np2;
-                ring_om[f & (R - 1)][lane] = vrom[v][lane];
+                ring_om[f & (R - 1)][lane] = fix_om;
                 t_run = f + 1;
                 if (lane == 0) { run_t = f; fail_t = STR_NONE; }
             } else if (vi >= 0) {
