@@ -293,3 +293,34 @@ def test_out_of_range_symbol_is_rejected_by_the_library(engine):
     engine.set_model(m["a"], m["b"], m["pi"])
     ref = hoc.loglik_blocks(m["a"], ho.emission_table(m["b"]), m["pi"], [sym[:3000].astype(np.int64), sym[3000:].astype(np.int64)])
     np.testing.assert_allclose(engine.loglik(per_block=True)[1][0], ref, rtol=LL_RTOL)
+
+
+def test_viterbi_stream_under_concurrency_is_stable(engine):
+    """Regression: the decoupled Viterbi sweep synchronises its warps through shared-memory
+    flags; a race in its roll-back phase only showed when other kernels (posterior,
+    log-likelihood) ran beside it.  100 chains, the three recursions overlapped, repeated:
+    every repetition must give the same bit-exact paths."""
+    m = golden("model_3_3_example.npz")
+    a, b, pi = m["a"], m["b"], m["pi"]
+    rng = np.random.default_rng(2026)
+    V_lst = [ho.sample_block(a, b, pi, int(T), rng, p_n=0.01) for T in rng.integers(15000, 30000, size=100)]
+    engine.load_blocks(V_lst)
+    engine.set_model(a, b, pi)
+    LA, LE, om0 = _tables(a, b, pi, V_lst)
+    ref = hoc.viterbi_blocks(LA, LE, om0, V_lst[:6])
+    first = None
+    engine.set_async(True)
+    try:
+        for rep in range(8):
+            path = engine.viterbi(LA, LE, om0)
+            engine.posterior(fetch=False)
+            engine.loglik()
+            engine.sync()
+            if first is None:
+                first = path.copy()
+                for p, r in zip(engine.split(path)[:6], ref):
+                    assert np.array_equal(p, r)
+            else:
+                assert np.array_equal(path, first), f"repetition {rep}"
+    finally:
+        engine.set_async(False)
