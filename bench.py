@@ -48,10 +48,35 @@ WORKLOADS = {
 
 # ---------------------------------------------------------------------------------
 def sample_clocks(stop, out, gpu_index):
+    """SM clock and throttle reasons DURING the timed region.  NVML (a few samples per
+    step) when the bindings are importable, else the nvidia-smi query of the profiling recipe."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (0x8, 0x40, 0x20, 0x4)     # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap (nvml.h)
+        n_ok = 0
+        while True:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                r = int(reasons_fn(h))
+            except Exception:
+                r = 0
+            out.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b in bits])
+            n_ok += 1
+            if stop.is_set():
+                break
+            stop.wait(0.004)
+        return
+    except Exception as e:
+        print(f"[bench] NVML clock sampling unavailable ({type(e).__name__}: {e}); using nvidia-smi", file=sys.stderr)
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    while not stop.is_set():
+    while True:                      # (at least one sample, even for a very short timed region)
         try:
             r = subprocess.run(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}",
                                 "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
@@ -60,6 +85,8 @@ def sample_clocks(stop, out, gpu_index):
                 out.append(f)
         except Exception:
             pass
+        if stop.is_set():
+            break
         stop.wait(0.2)
 
 
@@ -365,6 +392,8 @@ def main():
                          "optimizer.py:146-354 (oracle/hmm_oracle.c), one pass, all host threads over blocks",
                "breakdown": {k: ncs / max(v, 1e-12) for k, v in zip(("forward", "viterbi", "posterior"), parts)}}
 
+    if th.is_alive():
+        th.join(timeout=10)
     line = {
         "metric": "alignment columns/sec (forward loglik + Viterbi + posterior)",
         "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
