@@ -186,6 +186,7 @@ int itr_csv_format_double(double x, char *out, int cap);
  * valid after itr_sync(ctx).  Device-to-host copies overlap only into page-locked
  * buffers; into pageable memory they complete before the call returns.  Changing the
  * blocks or the model always waits for enqueued work first. */
+/* In deferred mode itr_build_model with a == b == pi == NULL also only enqueues the build. */
 int itr_set_async(itr_ctx *ctx, int on);
 int itr_sync(itr_ctx *ctx);
 

@@ -568,7 +568,9 @@ extern "C" int itr_build_model(itr_ctx *ctx, int n_sets, const double *params, i
     if (pi) CK(cudaMemcpyAsync(pi, d_pi, (size_t)n_sets * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     rc = install_model_device(ctx, n_sets, K, d_a, d_b, d_pi);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    // Deferred mode without host outputs: the build is only enqueued; the recursions that
+    // use the model wait for ev_ready on the device, itr_viterbi (which does not) overlaps it.
+    if (!(ctx->async && !a && !b && !pi)) CK(cudaStreamSynchronize(ctx->stream));
     return ITR_OK;
 }
 
@@ -964,7 +966,9 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
     CK(ensure(ctx->d_path, ctx->cap_path, (size_t)ctx->n_cols));
     CK(ensure(ctx->d_final, ctx->cap_final, (size_t)nb));
     double *t_la = ctx->d_tmp, *t_le = t_la + n_la, *t_om = t_le + n_le;
-    CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    // No wait for ev_ready: this recursion reads only the resident blocks (installed
+    // synchronously) and the caller's log tables, nothing of the device model — so it
+    // overlaps a model build that is still in flight (itr_build_model in the same step).
     // A posterior on its way to the host is PCIe bound (2 GB); its kernels go first, so
     // that the download starts early, and this recursion runs under the transfer.
     if (ctx->post_download) CK(cudaStreamWaitEvent(st, ctx->ev_post_compute, 0));
