@@ -990,7 +990,7 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
         CK(chunk_smem(viterbi_traceback_kernel, (size_t)VCHUNK * KP + VCHUNK, &w2, &sh2));
         viterbi_compose_kernel<<<blocks_for((size_t)ctx->n_chunks, w1), w1 * 32, sh1, st>>>(
             ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, KP, K, ctx->n_chunks, ctx->d_comp);
-        viterbi_boundary_kernel<<<blocks_for((size_t)nb, 128), 128, 0, st>>>(ctx->d_off, ctx->d_chunk_off, ctx->d_comp,
+        viterbi_boundary_kernel<<<blocks_for((size_t)nb, VB_WARPS), 32 * VB_WARPS, 0, st>>>(ctx->d_off, ctx->d_chunk_off, ctx->d_comp,
                                                                             ctx->d_final, KP, (int)nb, ctx->d_chunk_end);
         viterbi_traceback_kernel<<<blocks_for((size_t)ctx->n_chunks, w2), w2 * 32, sh2, st>>>(
             ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, ctx->d_chunk_end, KP, ctx->n_chunks, ctx->d_path);
