@@ -199,6 +199,32 @@ def optimization_wrapper(arg_lst, optimized_params, case, d, V_lst, res_name, in
     return -loglik
 
 
+def loglik_sweep(arg_sets, optimized_params, case, d, V_lst):
+    """Log-likelihoods of MANY parameter vectors in one batched device call: the objective of
+    ``optimization_wrapper`` (optimizer.py:396-567: parameter vector -> derived times ->
+    model build -> summed forward log-likelihood) for every row of ``arg_sets``
+    (n_sets x len(optimized_params)), without the history / best-model side effects.
+    One batched model build (FP64 tensor cores) and one multi-set forward sweep over the
+    resident blocks; the building block of a batched-simplex or multi-start optimiser
+    (SURVEY 8f N3).  Returns a float64 vector of length n_sets."""
+    arg_sets = np.atleast_2d(np.asarray(arg_sets, dtype=np.float64))
+    if arg_sets.shape[1] != len(optimized_params):
+        raise ValueError("arg_sets must have one column per optimised parameter")
+    rows = []
+    for args in arg_sets:
+        d_copy = d.copy()
+        for i, param in enumerate(optimized_params):
+            d_copy[param] = float(args[i])
+        derive_times(d_copy, case)
+        rows.append(model_args(d_copy))
+    eng, _ = _resident(V_lst)
+    eng.build_model(np.array(rows, dtype=np.float64), d["n_int_AB"], d["n_int_ABC"], fetch=False)
+    total = eng.loglik()
+    if dist_.is_active():
+        total = dist_.allreduce_sum(total, eng.device)
+    return np.asarray(total, dtype=np.float64)
+
+
 def optimizer(optim_variables, optim_list, bounds, fixed_params, V_lst, res_name, case,
               method="Nelder-Mead", header=True):
     """scipy.optimize.minimize over the scaled parameters (optimizer.py:586-637)."""

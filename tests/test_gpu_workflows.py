@@ -90,3 +90,33 @@ def test_optimize_then_decode(small_maf, engine):
         assert open(out_native, "rb").read() == open(out_py, "rb").read()
     engine_cache._ENGINE = None
     engine_cache._LOADED = None
+
+
+def test_loglik_sweep_equals_single_evaluations(small_maf, engine, tmp_path):
+    """Batched objective (one batched model build + one multi-set forward sweep) against the
+    per-point objective `optimization_wrapper` (optimizer.py:396-583)."""
+    from itrails_b200 import engine_cache
+    from itrails_b200.optimizer import loglik_sweep, optimization_wrapper
+    from itrails_b200.workflows import prepare_optimize
+    _maf, V_lst, _d = small_maf
+    cfg = {"fixed_parameters": {"mu": 1e-8, "t_1": 240000, "t_2": 40000, "t_upper": 745069.3855, "N_ABC": 50000},
+           "optimized_parameters": {"N_AB": [40000, 5000, 500000], "r": [2e-8, 1e-9, 1e-7]}}
+    optim_variables, optim_list, bounds, fixed, case = prepare_optimize(cfg, 2, 2)
+    engine_cache._ENGINE = engine
+    try:
+        rng = np.random.default_rng(4)
+        lo = np.array([b[0] for b in bounds]); hi = np.array([b[1] for b in bounds])
+        pts = np.vstack([optim_list] + [lo * (hi / lo) ** rng.random(len(lo)) for _ in range(6)])
+        batched = loglik_sweep(pts, optim_variables, case, fixed, V_lst)
+        assert batched.shape == (7,)
+        res = str(tmp_path / "run")
+        with open(res + ".best_model.yaml", "w") as fh:      # the workflow creates it before optimising
+            yaml.safe_dump({"fixed_parameters": {"mu": 1e-8}, "optimized_parameters": {},
+                            "results": {"log_likelihood": None, "iteration": None}}, fh)
+        info = {"Nfeval": 0, "time": 0.0}
+        single = np.array([-optimization_wrapper(p, optim_variables, case, fixed, V_lst, res, info) for p in pts])
+        np.testing.assert_allclose(batched, single, rtol=1e-12)
+        assert len(set(np.round(single, 3))) > 1
+    finally:
+        engine_cache._ENGINE = None
+        engine_cache._LOADED = None

@@ -15,7 +15,7 @@ a, b, pi, _ = eng.build_model(args[None, :], 3, 3)
 lens = synth.block_lengths(100, 10_000_000, rng)
 V = synth.alignment(a[0], b[0], pi[0], lens, 7)
 eng.load_blocks(V)
-for n_sets in (1, 64, 256):
+for n_sets in (1, 64, 256, 1024):
     P = np.repeat(args[None, :], n_sets, axis=0) * np.exp(rng.uniform(-0.2, 0.2, size=(n_sets, 9)))
     P[:, 2] = (P[:, 0] + P[:, 1]) / 2 + P[:, 3]
     eng.build_model(P, 3, 3, fetch=False); eng.loglik()
