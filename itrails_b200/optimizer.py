@@ -225,6 +225,30 @@ def loglik_sweep(arg_sets, optimized_params, case, d, V_lst):
     return np.asarray(total, dtype=np.float64)
 
 
+def _optimizer_batched(optim_variables, optim_list, bounds, d, V_lst, res_name, case):
+    """Nelder-Mead with one batched objective call per iteration (batched_simplex.py): the
+    reflection / expansion / contraction candidates of an iteration are evaluated together by
+    ``loglik_sweep``; the history and best-model files receive exactly the evaluations, in the
+    order, the sequential search (optimizer.py:623-637) makes."""
+    from .batched_simplex import minimize_neldermead_batched
+
+    output_dir, output_prefix = os.path.split(res_name)
+    history = os.path.join(output_dir, f"{output_prefix}.optimization_history.csv")
+    best_model_yaml = os.path.join(output_dir, f"{output_prefix}.best_model.yaml")
+    rank, _world = dist_.rank_world()
+    info = {"Nfeval": 0, "time": time.time()}
+
+    def consume(x, f):
+        if rank == 0:
+            write_list([info["Nfeval"]] + np.asarray(x).tolist() + [-f, time.time() - info["time"]], history)
+            update_best_model(best_model_yaml, optim_variables, x, -f, info["Nfeval"])
+        info["Nfeval"] += 1
+
+    return minimize_neldermead_batched(
+        lambda X: -loglik_sweep(X, optim_variables, case, d, V_lst),
+        optim_list, bounds=bounds, maxiter=10000, consume=consume, disp=True)
+
+
 def optimizer(optim_variables, optim_list, bounds, fixed_params, V_lst, res_name, case,
               method="Nelder-Mead", header=True):
     """scipy.optimize.minimize over the scaled parameters (optimizer.py:586-637)."""
@@ -235,6 +259,8 @@ def optimizer(optim_variables, optim_list, bounds, fixed_params, V_lst, res_name
     rank, _world = dist_.rank_world()
     if header and rank == 0:
         write_list(["n_eval"] + list(optim_variables) + ["loglik", "time"], history)
+    if method == "Nelder-Mead-batched":
+        return _optimizer_batched(optim_variables, optim_list, bounds, fixed_params.copy(), V_lst, res_name, case)
     return minimize(
         optimization_wrapper,
         x0=optim_list,

@@ -179,7 +179,10 @@ def optimize_main(argv=None):
     settings["output_prefix"], settings["input_maf"] = user_output, maf_path
     mu = float(config["fixed_parameters"]["mu"])
     method = str(settings["method"]).lower()
-    if method not in ("nelder-mead", "l-bfgs-b"):
+    # 'nelder-mead-batched' is this package's addition: the same simplex search with the
+    # candidates of an iteration evaluated in one batched device call (batched_simplex.py)
+    methods = {"nelder-mead": "Nelder-Mead", "l-bfgs-b": "L-BFGS-B", "nelder-mead-batched": "Nelder-Mead-batched"}
+    if method not in methods:
         raise ValueError("Method must be one of ['nelder-mead', 'l-bfgs-b'].")
     print(f"Using optimization method: {method}")
 
@@ -210,7 +213,7 @@ def optimize_main(argv=None):
     print("Running optimization...")
     res = optimizer(optim_variables=optim_variables, optim_list=optim_list, bounds=bounds_list,
                     fixed_params=fixed_dict, V_lst=maf_alignment, res_name=user_output, case=case,
-                    method="Nelder-Mead" if method == "nelder-mead" else "L-BFGS-B", header=True)
+                    method=methods[method], header=True)
     print(f"Optimization complete. Results saved to "
           f"{os.path.join(output_dir, f'{output_prefix}.optimization_history.csv')}.\n"
           f" Best model saved to {best_model_yaml}.")

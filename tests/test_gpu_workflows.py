@@ -120,3 +120,44 @@ def test_loglik_sweep_equals_single_evaluations(small_maf, engine, tmp_path):
     finally:
         engine_cache._ENGINE = None
         engine_cache._LOADED = None
+
+
+def test_batched_nelder_mead_workflow_matches_sequential(small_maf, engine):
+    """`method: nelder-mead-batched` (speculative simplex, one batched objective call per
+    iteration) against `method: Nelder-Mead` (scipy, one call per evaluation, as
+    optimizer.py:623-637): same evaluations in the same order, same optimum."""
+    import time
+    from itrails_b200 import engine_cache, workflows
+    maf, _V_lst, d = small_maf
+    cfg = {"fixed_parameters": {"mu": 1e-8, "t_1": 240000, "t_2": 40000, "t_upper": 745069.3855, "N_ABC": 50000},
+           "optimized_parameters": {"N_AB": [40000, 5000, 500000], "r": [2e-8, 1e-9, 1e-7]},
+           "settings": {"input_maf": None, "output_prefix": None, "n_cpu": 4, "method": "Nelder-Mead",
+                        "species_list": SPECIES, "n_int_AB": 2, "n_int_ABC": 2}}
+    engine_cache._ENGINE = engine
+    try:
+        out, wall = {}, {}
+        for method in ("Nelder-Mead", "nelder-mead-batched"):
+            cfg["settings"]["method"] = method
+            cfg_path = os.path.join(d, f"cfg_{method}.yaml")
+            with open(cfg_path, "w") as fh:
+                yaml.safe_dump(cfg, fh)
+            prefix = os.path.join(d, "out_nm", method)
+            t0 = time.perf_counter()
+            res = workflows.optimize_main([cfg_path, "--input", maf, "--output", prefix])
+            wall[method] = time.perf_counter() - t0
+            hist = list(csv.reader(open(prefix + ".optimization_history.csv")))
+            out[method] = (res, np.array([[float(v) for v in r[:4]] for r in hist[1:]]),
+                           yaml.safe_load(open(prefix + ".best_model.yaml")))
+        (rs, hs, bs), (rb, hb, bb) = out["Nelder-Mead"], out["nelder-mead-batched"]
+        assert rb.nfev == rs.nfev and rb.nit == rs.nit and hb.shape == hs.shape
+        np.testing.assert_array_equal(hb[:, 0], hs[:, 0])
+        np.testing.assert_allclose(hb[:, 1:3], hs[:, 1:3], rtol=1e-12)        # parameter vectors
+        np.testing.assert_allclose(hb[:, 3], hs[:, 3], rtol=1e-12)            # log-likelihoods
+        np.testing.assert_allclose(rb.x, rs.x, rtol=1e-12)
+        assert bb["results"]["iteration"] == bs["results"]["iteration"]
+        assert rb.nbatch < rs.nfev
+        print(f"nelder-mead {wall['Nelder-Mead']:.3f} s ({rs.nfev} evaluations), "
+              f"batched {wall['nelder-mead-batched']:.3f} s ({rb.nbatch} calls, {rb.nspec} points)")
+    finally:
+        engine_cache._ENGINE = None
+        engine_cache._LOADED = None

@@ -488,3 +488,55 @@ def test_native_posterior_csv_is_byte_identical_to_csv_writer(tmp_path):
                 w.writerow([bi, int(pos[r]) if positions is not None else r - off[bi]] + post[r].tolist())
         assert open(p, "rb").read() == s.getvalue().encode()
     assert lib.itr_csv_posterior_host(str(tmp_path / "no" / "dir.csv").encode(), K, 0, None, None, None, 1) == _lib.ITR_ERR_IO
+
+
+# ---------------------------------------------------------------------------
+# Speculative (batched) Nelder-Mead against the sequential search the reference runs
+# (scipy.optimize.minimize(method="Nelder-Mead", bounds=...), optimizer.py:623-637)
+# ---------------------------------------------------------------------------
+def _nm_objectives():
+    def rosen(x):
+        return float(np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2))
+
+    def crinkled(x):                      # non-smooth: forces contractions and shrinks
+        return float(np.sum(np.abs(x - 0.3)) + 0.5 * np.abs(np.sin(7 * x)).sum() + np.max(np.abs(x)))
+
+    def zero_start(x):
+        return float(np.sum((x - np.array([0.5, -0.25, 2.0])) ** 2))
+    return [
+        (rosen, np.array([-1.2, 1.0, 0.8, 1.9, -0.5]), [(-2.0, 2.0)] * 5, {}),
+        (rosen, np.array([1.99, 1.0, 0.8]), [(-2.0, 2.0)] * 3, {}),          # simplex reflected at the upper bound
+        (crinkled, np.array([1.0, -1.0, 0.5, 0.25]), [(-1.5, 1.5)] * 4, {}),
+        (crinkled, np.array([1.0, -1.0, 0.5, 0.25]), None, {"maxiter": 40}),
+        (crinkled, np.array([1.0, -1.0, 0.5, 0.25]), [(-1.5, 1.5)] * 4, {"maxfev": 37}),
+        (crinkled, np.array([1.0, -1.0]), [(-1.5, 1.5)] * 2, {"maxfev": 2}),
+        (zero_start, np.array([0.0, 0.0, 1.0]), [(-3.0, 3.0)] * 3, {"maxiter": 10000}),
+    ]
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_batched_nelder_mead_reproduces_sequential_search(case):
+    import warnings
+    from scipy.optimize import minimize
+    from itrails_b200.batched_simplex import minimize_neldermead_batched
+    fun, x0, bounds, opts = _nm_objectives()[case]
+    seq = []
+
+    def logged(x):
+        f = fun(x)
+        seq.append((np.array(x, copy=True), f))
+        return f
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = minimize(logged, x0, method="Nelder-Mead", bounds=bounds, options=dict(opts))
+    got = []
+    res = minimize_neldermead_batched(lambda X: [fun(x) for x in X], x0, bounds=bounds,
+                                      consume=lambda x, f: got.append((np.array(x, copy=True), f)), **opts)
+    assert res.nfev == ref.nfev == len(got) == len(seq)
+    assert res.nit == ref.nit and res.status == ref.status
+    for (xa, fa), (xb, fb) in zip(got, seq):
+        assert np.array_equal(xa, xb) and fa == fb
+    assert np.array_equal(res.x, ref.x) and res.fun == ref.fun
+    assert np.array_equal(res.final_simplex[0], ref.final_simplex[0])
+    if ref.nit > 5:
+        assert res.nbatch < ref.nfev            # fewer dependent objective calls than evaluations
