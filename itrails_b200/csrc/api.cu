@@ -805,14 +805,14 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
 static int prepare_runs(itr_ctx *ctx, cudaStream_t st) {
     if (ctx->runs_valid) return ITR_OK;
     const int KP = ctx->KP;
-    CK(ensure(ctx->d_P, ctx->cap_P, (size_t)ctx->n_sets * RUN_POWERS * KP * KP));
-    CK(ensure(ctx->d_sP, ctx->cap_sP, (size_t)ctx->n_sets * RUN_POWERS));
+    CK(ensure(ctx->d_P, ctx->cap_P, (size_t)ctx->n_sets * RUN_TABLE * KP * KP));
+    CK(ensure(ctx->d_sP, ctx->cap_sP, (size_t)ctx->n_sets * RUN_TABLE));
     CK(ensure(ctx->d_ebar, ctx->cap_ebar, (size_t)ctx->n_sets * KP));
     symbol_class_kernel<<<1, 640, 0, st>>>(ctx->d_Et, ctx->K, KP, ctx->n_sets, 1e-12, ctx->d_rep);
     pick_run_class_kernel<<<1, 640, 0, st>>>(ctx->d_hist, ctx->d_rep, ctx->d_isrun, ctx->d_runinfo);
     run_power_kernel<<<ctx->n_sets, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, 0, ctx->d_P, ctx->d_sP, ctx->d_ebar);
     // backward powers (diag(e) a)^(2^k) for parameter set 0 (the posterior decodes set 0)
-    CK(ensure(ctx->d_Pb, ctx->cap_Pb, (size_t)RUN_POWERS * KP * KP));
+    CK(ensure(ctx->d_Pb, ctx->cap_Pb, (size_t)RUN_TABLE * KP * KP));
     run_power_kernel<<<1, dim3(32, 32), 0, st>>>(ctx->d_A, ctx->d_Et, ctx->d_runinfo, KP, 1, ctx->d_Pb, nullptr, nullptr);
     ctx->launches += 4;
     CK(cudaGetLastError());
