@@ -277,6 +277,33 @@ def test_run_compressed_loglik_equals_plain_sweep(engine, monkeypatch):
     np.testing.assert_allclose(pb[0], hoc.loglik_blocks(a, ho.emission_table(b), pi, V_rand), rtol=LL_RTOL)
 
 
+def test_every_run_length_and_table_slot(engine):
+    """Runs of every length 1..70 of the dominant invariant column, at every alignment to
+    the 32-column tiles, separated by single literal columns: each slot of the run-power
+    table (2..8, 16, 24, 32 columns per step) and each two-step decomposition is used by the
+    log-likelihood sweep and by both checkpoint sweeps of the posterior; against the oracle."""
+    m = golden("model_3_3_example.npz")
+    a, b, pi = m["a"], m["b"], m["pi"]
+    rng = np.random.default_rng(33)
+    literals = np.array([1, 17, 64 + 16 + 4 + 1, 255, 256, 300, 624, 27])      # non-invariant and N symbols
+    blocks = []
+    for shift in (0, 5, 13, 31):
+        cols = [rng.integers(0, 256, size=shift + 1)]
+        for n in rng.permutation(np.arange(1, 71)):
+            cols.append(np.zeros(n, dtype=np.int64))                                # AAAA run
+            cols.append(literals[rng.integers(0, len(literals), size=1)])
+        blocks.append(np.concatenate(cols).astype(np.int64))
+    blocks.append(np.zeros(39, dtype=np.int64))
+    blocks.append(np.concatenate([np.zeros(24, dtype=np.int64), [300], np.zeros(7, dtype=np.int64)]))
+    engine.load_blocks(blocks)
+    engine.set_model(a, b, pi)
+    _, pb = engine.loglik(per_block=True)
+    np.testing.assert_allclose(pb[0], hoc.loglik_blocks(a, ho.emission_table(b), pi, blocks), rtol=LL_RTOL)
+    post = engine.split(engine.posterior())
+    for p_, r in zip(post, ho.post_prob_wrapper(a, b, pi, blocks)):
+        assert np.abs(p_ - r).max() <= POST_ATOL
+
+
 def test_out_of_range_symbol_is_rejected_by_the_library(engine):
     """list.index raises in the reference's maf_parser (read_data.py:113-115); through the
     C ABI a symbol > 624 is caught by the device-side range check of itr_load_blocks."""
