@@ -497,7 +497,7 @@ run_power_kernel(const double *__restrict__ A, const double *__restrict__ Et, co
 // Forward log-likelihood with run compression (K <= 32).  Same contract as
 // forward_kernel<KT, 1, true, 0>.
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(192)
 forward_runs_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ PI,
                     const double *__restrict__ Et, const double *__restrict__ P, const int32_t *__restrict__ sP,
                     const double *__restrict__ ebar, const uint8_t *__restrict__ isrun, int K,
@@ -608,7 +608,7 @@ constexpr int PTILE = 32;
 // DIR 0: forward checkpoints ck[tile] = alpha_{32 m - 1} (state entering tile m; tile 0 unused)
 // DIR 1: backward checkpoints ck[tile] = beta_{32 m + 31} (last tile of a block: not stored, it is 1)
 template <int KT, int DIR>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(192)
 checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ PI,
                         const double *__restrict__ Et, const double *__restrict__ P, const double *__restrict__ ebar,
                         const uint8_t *__restrict__ isrun, const int64_t *__restrict__ tile_off, int K,

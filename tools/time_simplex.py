@@ -57,7 +57,14 @@ with warnings.catch_warnings():
         opt.update_best_model(res + ".best_model.yaml", names, x, -f, info["Nfeval"])
         info["Nfeval"] += 1
         hist.append(f)
-    r_bat = minimize_neldermead_batched(lambda X: -opt.loglik_sweep(X, names, case, fixed, V), start,
+    calls = []
+
+    def batch(X):
+        t = time.perf_counter()
+        f = -opt.loglik_sweep(X, names, case, fixed, V)
+        calls.append((time.perf_counter() - t) * 1e3)
+        return f
+    r_bat = minimize_neldermead_batched(batch, start,
                                         bounds=bounds, maxiter=iters, consume=consume)
     t_bat = time.perf_counter() - t0
 
@@ -67,4 +74,6 @@ print(f"sequential Nelder-Mead: {r_seq.nit} iterations, {r_seq.nfev} evaluations
 print(f"batched   Nelder-Mead: {r_bat.nit} iterations, {r_bat.nfev} evaluations consumed, "
       f"{r_bat.nbatch} batched calls ({r_bat.nspec} points), {t_bat:.3f} s "
       f"({t_bat / r_bat.nit * 1e3:.2f} ms/iteration)")
+print(f"batched objective calls: median {np.median(calls):.2f} ms, max {max(calls):.2f} ms, sum {sum(calls):.0f} ms "
+      f"(the rest of the wall time is the history / best-model files)")
 print(f"same trajectory: {same}; -loglik {r_seq.fun:.6f} vs {r_bat.fun:.6f}; speed-up {t_seq / t_bat:.2f}x")
