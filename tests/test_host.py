@@ -398,10 +398,12 @@ def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
             def load_blocks(self, V_lst): self.V = list(V_lst); self.loads = getattr(self, "loads", 0) + 1
             def set_model(self, a, b, pi): self.m = (a, b, pi)
             def build_model(self, params, n_ab, n_abc, cut_AB=None, cut_ABC=None, fetch=True):
-                a, b, pi, hid, _ = co.trans_emiss_calc(*params[0], n_ab, n_abc)
-                self.m = (a, b, pi)
+                self.sets = [co.trans_emiss_calc(*row, n_ab, n_abc)[:3] for row in params]
+                self.m = self.sets[0]
                 return None, None, None, None
-            def loglik(self): return np.array([ho.loglik_wrapper(*self.m, self.V)])
+            def loglik(self):
+                sets = getattr(self, "sets", None) or [self.m]
+                return np.array([ho.loglik_wrapper(*m, self.V) for m in sets])
             def viterbi(self, log_a, log_E, omega0):
                 return np.concatenate([p for p in ho.viterbi_wrapper(*self.m, self.V)]).astype(np.uint8)
             def split(self, flat):
@@ -439,6 +441,30 @@ def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
         if rank == 0:
             lines = open(res + ".optimization_history.csv").read().strip().splitlines()
             assert len(lines) == 1 and lines[0].startswith("0,")
+        # batched simplex on the sharded objective: every rank walks the same simplex (the
+        # all-reduced values are identical), rank 0 alone writes the files; same evaluations
+        # as the sequential search
+        from scipy.optimize import minimize
+        case = frozenset(["t_A", "t_B", "t_C"])
+        bounds = [(d["N_AB"] * 0.2, d["N_AB"] * 5)]
+        res2 = os.path.join({str(tmp_path)!r}, "bat")
+        if rank == 0:
+            with open(res2 + ".best_model.yaml", "w") as fh:
+                yaml.dump({{"fixed_parameters": {{"mu": 1e-8}}, "optimized_parameters": {{}},
+                           "results": {{"log_likelihood": None, "iteration": None}}}}, fh)
+        dist.barrier()
+        rb = O.optimizer(["N_AB"], [d["N_AB"] * 1.3], bounds, d, V_lst, res2, case, method="Nelder-Mead-batched")
+        assert D.allreduce_max(float(rb.x[0])) == rb.x[0] and D.allreduce_max(-float(rb.x[0])) == -rb.x[0]   # identical on both ranks
+        seq = minimize(lambda x: -float(O.loglik_sweep([x], ["N_AB"], case, d, V_lst)[0]), [d["N_AB"] * 1.3],
+                       method="Nelder-Mead", bounds=bounds, options={{"maxiter": 10000}})
+        assert seq.nfev == rb.nfev and seq.nit == rb.nit and seq.x[0] == rb.x[0], (seq.nfev, rb.nfev)
+        assert rb.nbatch < rb.nfev
+        dist.barrier()
+        if rank == 0:
+            lines = open(res2 + ".optimization_history.csv").read().strip().splitlines()
+            assert lines[0] == "n_eval,N_AB,loglik,time" and len(lines) == rb.nfev + 1
+            best = yaml.safe_load(open(res2 + ".best_model.yaml"))
+            assert abs(best["results"]["log_likelihood"] + rb.fun) <= 1e-12 * abs(rb.fun)
         print("rank", rank, "ok")
     """))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
