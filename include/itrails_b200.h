@@ -160,6 +160,21 @@ int itr_posterior_fetch(itr_ctx *ctx, double *post);
  * CSV writer (workflow_posterior.py:697-716). */
 int itr_posterior_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, double *post);
 
+/* Posterior decoding streamed to the host (replaces post_prob_wrapper for results that
+ * do not fit in host memory: 250 Mb x 27 states = 54 GB).  The posterior is computed on
+ * the device in contiguous ranges of blocks and downloaded behind the computation in
+ * pieces of at most slot_cols columns (a piece never spans more than the ring slot) into
+ * ring[(piece % n_slots) * slot_cols * K ...]; ring holds n_slots * slot_cols * K doubles
+ * and should be page-locked.  sink (nullable) is called from the calling thread, in
+ * ascending column order, once per piece: rows = n_cols x K doubles for the columns
+ * [col0, col0 + n_cols) of the concatenated alignment; the slot is reused after it
+ * returns; a non-zero return stops the stream (ITR_ERR_IO).  With sink == NULL the pieces
+ * are only delivered into the ring.  The full result also stays on the device
+ * (itr_posterior_fetch_range). */
+typedef int (*itr_rows_sink)(void *user, int64_t col0, int64_t n_cols, const double *rows);
+int itr_posterior_stream(itr_ctx *ctx, double *ring, int64_t slot_cols, int n_slots,
+                         itr_rows_sink sink, void *user);
+
 /* ---- result writers (host C++, thread pool) --------------------------------------
  * Write `{prefix}.posterior.csv` exactly as the reference's csv.writer loop does
  * (workflow_posterior.py:697-716): header `alignment_block_idx,position_idx,prob_state_0…`,
@@ -172,9 +187,22 @@ int itr_posterior_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, double
  * itr_posterior block by block (download of block i+1 overlaps formatting of block i), so
  * a chromosome-scale result never has to exist in host memory. */
 int itr_posterior_write_csv(itr_ctx *ctx, const char *path, const int64_t *positions, int n_threads);
+/* Sharded form (one process per GPU, each holding an LPT share of the blocks;
+ * workflow_posterior.py:693-716 writes ONE file with global block indices): block_ids
+ * (nullable, one per loaded block) is the index printed for each block, write_header == 0
+ * leaves the header line out (a part file), block_bytes (nullable, one per loaded block)
+ * receives the bytes each block's rows took, so that the parts can be spliced in global
+ * block order. */
+int itr_posterior_write_csv_ex(itr_ctx *ctx, const char *path, const int64_t *positions,
+                               const int64_t *block_ids, int write_header, int64_t *block_bytes,
+                               int n_threads);
 /* The same writer on a host matrix (no GPU context needed): post is sum(T) x K. */
 int itr_csv_posterior_host(const char *path, int K, int64_t n_blocks, const int64_t *offsets,
                            const int64_t *positions, const double *post, int n_threads);
+/* Host-matrix writer with the sharded options of itr_posterior_write_csv_ex. */
+int itr_csv_posterior_host_ex(const char *path, int K, int64_t n_blocks, const int64_t *offsets,
+                              const int64_t *positions, const double *post, const int64_t *block_ids,
+                              int write_header, int64_t *block_bytes, int n_threads);
 /* repr(float) of one value into out (cap >= 32, NUL terminated); returns the length. */
 int itr_csv_format_double(double x, char *out, int cap);
 

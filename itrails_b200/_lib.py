@@ -54,7 +54,11 @@ SIGNATURES = {
     "itr_posterior_fetch": (ctypes.c_int, [_c_ctx, _dp]),
     "itr_posterior_fetch_range": (ctypes.c_int, [_c_ctx, ctypes.c_int64, ctypes.c_int64, _dp]),
     "itr_posterior_write_csv": (ctypes.c_int, [_c_ctx, ctypes.c_char_p, _i64p, ctypes.c_int]),
+    "itr_posterior_write_csv_ex": (ctypes.c_int, [_c_ctx, ctypes.c_char_p, _i64p, _i64p, ctypes.c_int, _i64p, ctypes.c_int]),
+    "itr_posterior_stream": (ctypes.c_int, [_c_ctx, _dp, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "itr_csv_posterior_host": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int64, _i64p, _i64p, _dp, ctypes.c_int]),
+    "itr_csv_posterior_host_ex": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int64, _i64p, _i64p, _dp, _i64p,
+                                                 ctypes.c_int, _i64p, ctypes.c_int]),
     "itr_csv_format_double": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p, ctypes.c_int]),
     "itr_set_async": (ctypes.c_int, [_c_ctx, ctypes.c_int]),
     "itr_sync": (ctypes.c_int, [_c_ctx]),
@@ -76,6 +80,9 @@ SIGNATURES = {
                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                        ctypes.POINTER(ctypes.c_int)]),
 }
+
+# int sink(void *user, int64_t col0, int64_t n_cols, const double *rows)
+ROWS_SINK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _dp)
 
 _lib = None
 

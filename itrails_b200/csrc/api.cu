@@ -42,6 +42,8 @@ struct itr_ctx {
     bool async = false;
     double *pend_total = nullptr, *pend_per_block = nullptr;   // host outputs of a deferred itr_loglik
     bool pend_ll = false;
+    int pend_sets = 0;                 // shape of the pending request (snapshot at call time)
+    int64_t pend_blocks = 0;
     cudaDeviceProp prop{};
     std::string err;
     int64_t launches = 0;
@@ -64,6 +66,11 @@ struct itr_ctx {
     std::vector<int64_t> h_tile_off;
     std::vector<cudaStream_t> grp_streams;     // 2 per posterior group
     std::vector<cudaEvent_t> grp_events;       // 2 per posterior group
+    // itr_posterior_stream: pass 2 runs in `stream_ranges` contiguous block ranges; range r is
+    // complete at range_events[r] and ends at column range_col_end[r]
+    int stream_ranges = 0;
+    std::vector<cudaEvent_t> range_events;
+    std::vector<int64_t> range_col_end;
 
     // model
     int n_sets = 0, K = 0, KP = 0;
@@ -249,6 +256,7 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
     if (ctx->h_ll) cudaFreeHost(ctx->h_ll);
     for (cudaStream_t st : ctx->grp_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : ctx->grp_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->range_events) cudaEventDestroy(ev);
     void *ptrs[] = {ctx->d_sym, ctx->d_off, ctx->d_order, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_queue,
                     ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_braw, ctx->d_digits, ctx->d_ll, ctx->d_LA,
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
@@ -853,17 +861,22 @@ static int need_ready(itr_ctx *ctx, const char *who) {
 // buffers: the reference accumulates block results in block order (optimizer.py:112-113).
 static void finish_loglik(itr_ctx *ctx) {
     if (!ctx->pend_ll) return;
-    const size_t n = (size_t)ctx->n_sets * ctx->n_blocks;
+    // shape as it was when the request was made: the blocks or the model may have been
+    // replaced since (both drain the streams first, then land here)
+    const int n_sets = ctx->pend_sets;
+    const int64_t n_blocks = ctx->pend_blocks;
+    const size_t n = (size_t)n_sets * n_blocks;
     if (ctx->pend_per_block) memcpy(ctx->pend_per_block, ctx->h_ll, n * sizeof(double));
     if (ctx->pend_total) {
-        for (int s = 0; s < ctx->n_sets; ++s) {
+        for (int s = 0; s < n_sets; ++s) {
             double acc = 0.0;
-            const double *p = ctx->h_ll + (size_t)s * ctx->n_blocks;
-            for (int64_t b = 0; b < ctx->n_blocks; ++b) acc += p[b];
+            const double *p = ctx->h_ll + (size_t)s * n_blocks;
+            for (int64_t b = 0; b < n_blocks; ++b) acc += p[b];
             ctx->pend_total[s] = acc;
         }
     }
     ctx->pend_ll = false;
+    ctx->pend_total = ctx->pend_per_block = nullptr;
 }
 
 // ---------------------------------------------------------------------------------
@@ -924,6 +937,8 @@ extern "C" int itr_loglik(itr_ctx *ctx, double *total, double *per_block) {
     CK(cudaMemcpyAsync(ctx->h_ll, ctx->d_ll, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     ctx->pend_total = total;
     ctx->pend_per_block = per_block;
+    ctx->pend_sets = ctx->n_sets;
+    ctx->pend_blocks = ctx->n_blocks;
     ctx->pend_ll = true;
     if (!ctx->async) {
         CK(cudaStreamSynchronize(st));
@@ -1028,6 +1043,63 @@ extern "C" int itr_viterbi_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_col
 }
 
 // ---------------------------------------------------------------------------------
+// two-pass posterior launches (K <= 32, run-dominated alignments)
+// ---------------------------------------------------------------------------------
+#define ITR_SWITCH_KT(K, M)             \
+    switch (((K) + 3) / 4) {            \
+        case 1: M(4); break;            \
+        case 2: M(8); break;            \
+        case 3: M(12); break;           \
+        case 4: M(16); break;           \
+        case 5: M(20); break;           \
+        case 6: M(24); break;           \
+        case 7: M(28); break;           \
+        default: M(32); break;          \
+    }
+
+// Pass 1, one direction (dir 0: forward checkpoints, 1: backward) over the chains of `cs`.
+static void launch_checkpoint_sweep(itr_ctx *ctx, int dir, const ChainSet &cs, cudaStream_t st) {
+    const int K = ctx->K, KP = ctx->KP;
+    const Geometry g = geometry(ctx, cs.n_blocks, 12);
+    const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+    reset_queue(cs.queue, st);
+#define CKS(KT)                                                                                                      \
+    do {                                                                                                             \
+        if (dir)                                                                                                     \
+            checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb,  \
+                                                                             ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
+        else                                                                                                         \
+            checkpoint_sweep_kernel<KT, 0><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P,   \
+                                                                             ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_a); \
+    } while (0)
+    ITR_SWITCH_KT(K, CKS)
+#undef CKS
+    ctx->launches += 1;
+}
+
+// Pass 2 over the tiles [t0, t1) (tile ids follow the input block order).
+static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t t0, int64_t t1) {
+    if (t1 <= t0) return cudaSuccess;
+    const int K = ctx->K, KP = ctx->KP;
+    const int wt = 4;
+    const size_t sht = (size_t)wt * (2 * KP + PTILE * (KP + 1) + PTILE) * sizeof(double);
+    const unsigned gt = (unsigned)std::min<int64_t>((t1 - t0 + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6);
+    cudaError_t e = cudaSuccess;
+#define PT2(KT)                                                                                                      \
+    do {                                                                                                             \
+        e = cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht); \
+        if (e == cudaSuccess)                                                                                        \
+            posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, t0, t1, \
+                                                                 ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K,       \
+                                                                 ctx->d_post);                                       \
+    } while (0)
+    ITR_SWITCH_KT(K, PT2)
+#undef PT2
+    ctx->launches += 1;
+    return e;
+}
+
+// ---------------------------------------------------------------------------------
 // posterior
 // ---------------------------------------------------------------------------------
 extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
@@ -1051,8 +1123,6 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         phase_begin(ctx, ITR_PH_POST_TOTAL, st);
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        const int wt = 4;
-        const size_t sht = (size_t)wt * (2 * KP + PTILE * (KP + 1) + PTILE) * sizeof(double);
         // Device destination: one pair of sweeps over all blocks, then one pass-2 launch.
         // Host destination: blocks are independent, so they run in groups of similar
         // length (contiguous ranges of the longest-first order), shortest group first,
@@ -1062,7 +1132,7 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         // hides the long blocks' latency-bound sweeps.
         const int nb = (int)ctx->n_blocks;
         // (with hundreds of chains the sweeps fill the GPU by themselves: one group, one pass-2 launch)
-        const int n_groups = (getenv("ITR_POST_ONE_GROUP") || (!post && nb > 256)) ? 1 : std::min(8, std::max(1, nb / 2));
+        const int n_groups = (getenv("ITR_POST_ONE_GROUP") || ctx->stream_ranges > 0 || (!post && nb > 256)) ? 1 : std::min(8, std::max(1, nb / 2));
         while ((int)ctx->grp_streams.size() < 2 * 8 + 1) {
             cudaStream_t s2 = nullptr;
             cudaEvent_t e2 = nullptr;
@@ -1079,100 +1149,87 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
         }
         cudaStream_t scopy = ctx->grp_streams[16];
         cudaEvent_t ecopy = ctx->grp_events[16];
-#define POST2(KT)                                                                                                     \
-    do {                                                                                                              \
-        CK(cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht));  \
-        for (int gi = n_groups - 1; gi >= 0; --gi) {                                                                  \
-            const int first = (int)((int64_t)nb * gi / n_groups), last = (int)((int64_t)nb * (gi + 1) / n_groups);    \
-            if (last <= first) continue;                                                                              \
-            const bool whole = (n_groups == 1);                                                                       \
-            cudaStream_t sf = whole ? st : ctx->grp_streams[2 * gi], sb = whole ? ctx->stream2 : ctx->grp_streams[2 * gi + 1]; \
-            ChainSet cf = chain_set(ctx, 1, whole ? 3 : 24 + 2 * gi), cb = chain_set(ctx, 1, whole ? 1 : 25 + 2 * gi); \
-            cf.order += first; cf.n_blocks = last - first;                                                            \
-            cb.order += first; cb.n_blocks = last - first;                                                            \
-            const Geometry g = geometry(ctx, last - first, 12);                                                       \
-            const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);                                              \
-            if (!whole) {                                                                                             \
-                CK(cudaStreamWaitEvent(sf, ctx->ev_fork, 0));                                                         \
-                CK(cudaStreamWaitEvent(sb, ctx->ev_fork, 0));                                                         \
-            }                                                                                                         \
-            reset_queue(cb.queue, sb);                                                   \
-            reset_queue(cf.queue, sf);                                                   \
-            if (gi == 0) phase_begin(ctx, ITR_PH_POST_BWD, sb);                                                       \
-            checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, sb>>>(                                         \
-                cb, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
-            if (gi == 0) phase_end(ctx, ITR_PH_POST_BWD, sb);                                                         \
-            if (gi == 0) phase_begin(ctx, ITR_PH_POST_FWD, sf);                                                       \
-            checkpoint_sweep_kernel<KT, 0><<<g.grid, g.warps * 32, sh, sf>>>(                                         \
-                cf, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_a); \
-            if (gi == 0) phase_end(ctx, ITR_PH_POST_FWD, sf);                                                         \
-            ctx->launches += 2;                                                                                       \
-            CK(cudaEventRecord(whole ? ctx->ev_join : ctx->grp_events[2 * gi + 1], sb));                             \
-            CK(cudaStreamWaitEvent(sf, whole ? ctx->ev_join : ctx->grp_events[2 * gi + 1], 0));                       \
-        }                                                                                                             \
-        /* second loop: a download into pageable memory blocks the host, so every sweep is enqueued first */        \
-        for (int gi = n_groups - 1; gi >= 0; --gi) {                                                                  \
-            const int first = (int)((int64_t)nb * gi / n_groups), last = (int)((int64_t)nb * (gi + 1) / n_groups);    \
-            if (last <= first) continue;                                                                              \
-            const bool whole = (n_groups == 1);                                                                       \
-            cudaStream_t sf = whole ? st : ctx->grp_streams[2 * gi];                                                  \
-            if (whole) {                                                                                              \
-                phase_begin(ctx, ITR_PH_POST_COMBINE, st);                                                            \
-                const int64_t nt = ctx->n_tiles;                                                                      \
-                const unsigned gt = (unsigned)std::min<int64_t>((nt + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6); \
-                posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
-                                                                     0, nt, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a,  \
-                                                                     ctx->d_ck_b, K, ctx->d_post);                     \
-                ctx->launches += 1;                                                                                   \
-                phase_end(ctx, ITR_PH_POST_COMBINE, st);                                                              \
-                if (post) {                                                                                           \
-                    CK(cudaEventRecord(ecopy, st));                                                                   \
-                    CK(cudaStreamWaitEvent(scopy, ecopy, 0));                                                         \
-                    CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, scopy));        \
-                }                                                                                                     \
-            } else {                                                                                                  \
-                /* pass 2 and download block by block, in the group's forward stream */                              \
-                if (gi == 0) phase_begin(ctx, ITR_PH_POST_COMBINE, sf);                                               \
-                for (int q = last - 1; q >= first; --q) {                                                             \
-                    const int32_t blk = ctx->h_order[q];                                                              \
-                    const int64_t t0 = ctx->h_tile_off[blk], t1 = ctx->h_tile_off[blk + 1];                           \
-                    if (t1 <= t0) continue;                                                                           \
-                    const unsigned gt = (unsigned)std::min<int64_t>((t1 - t0 + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6); \
-                    posterior_tiles_kernel<KT><<<gt, wt * 32, sht, sf>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, \
-                                                                         t0, t1, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, \
-                                                                         ctx->d_ck_b, K, ctx->d_post);                 \
-                    ctx->launches += 1;                                                                               \
-                    if (!post) continue;                                                                              \
-                    CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));                                                 \
-                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sf); ctx->tr_k.push_back(e); } \
-                    CK(cudaStreamWaitEvent(scopy, ctx->grp_events[2 * gi], 0));                                       \
-                    const size_t o = (size_t)ctx->h_off[blk] * K, len = (size_t)(ctx->h_off[blk + 1] - ctx->h_off[blk]) * K; \
-                    CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, scopy)); \
-                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, scopy); ctx->tr_c.push_back(e); ctx->tr_b.push_back(blk); } \
-                }                                                                                                     \
-                if (gi == 0) phase_end(ctx, ITR_PH_POST_COMBINE, sf);                                                 \
-                if (post) {                        /* stream2 collects "kernels done" of every group */              \
-                    CK(cudaEventRecord(ctx->grp_events[2 * gi + 1], sf));                                             \
-                    CK(cudaStreamWaitEvent(ctx->stream2, ctx->grp_events[2 * gi + 1], 0));                            \
-                }                                                                                                     \
-                if (!post) {                       /* join the group into the copy stream's place: st waits below */ \
-                    CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));                                                 \
-                    CK(cudaStreamWaitEvent(st, ctx->grp_events[2 * gi], 0));                                          \
-                }                                                                                                     \
-            }                                                                                                         \
-        }                                                                                                             \
-    } while (0)
-        switch ((K + 3) / 4) {
-            case 1: POST2(4); break;
-            case 2: POST2(8); break;
-            case 3: POST2(12); break;
-            case 4: POST2(16); break;
-            case 5: POST2(20); break;
-            case 6: POST2(24); break;
-            case 7: POST2(28); break;
-            default: POST2(32); break;
+        for (int gi = n_groups - 1; gi >= 0; --gi) {
+            const int first = (int)((int64_t)nb * gi / n_groups), last = (int)((int64_t)nb * (gi + 1) / n_groups);
+            if (last <= first) continue;
+            const bool whole = (n_groups == 1);
+            cudaStream_t sf = whole ? st : ctx->grp_streams[2 * gi], sb = whole ? ctx->stream2 : ctx->grp_streams[2 * gi + 1];
+            ChainSet cf = chain_set(ctx, 1, whole ? 3 : 24 + 2 * gi), cb = chain_set(ctx, 1, whole ? 1 : 25 + 2 * gi);
+            cf.order += first; cf.n_blocks = last - first;
+            cb.order += first; cb.n_blocks = last - first;
+            if (!whole) {
+                CK(cudaStreamWaitEvent(sf, ctx->ev_fork, 0));
+                CK(cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
+            }
+            if (gi == 0) phase_begin(ctx, ITR_PH_POST_BWD, sb);
+            launch_checkpoint_sweep(ctx, 1, cb, sb);
+            if (gi == 0) phase_end(ctx, ITR_PH_POST_BWD, sb);
+            if (gi == 0) phase_begin(ctx, ITR_PH_POST_FWD, sf);
+            launch_checkpoint_sweep(ctx, 0, cf, sf);
+            if (gi == 0) phase_end(ctx, ITR_PH_POST_FWD, sf);
+            CK(cudaEventRecord(whole ? ctx->ev_join : ctx->grp_events[2 * gi + 1], sb));
+            CK(cudaStreamWaitEvent(sf, whole ? ctx->ev_join : ctx->grp_events[2 * gi + 1], 0));
         }
-#undef POST2
+        // second loop: a download into pageable memory blocks the host, so every sweep is enqueued first
+        for (int gi = n_groups - 1; gi >= 0; --gi) {
+            const int first = (int)((int64_t)nb * gi / n_groups), last = (int)((int64_t)nb * (gi + 1) / n_groups);
+            if (last <= first) continue;
+            const bool whole = (n_groups == 1);
+            cudaStream_t sf = whole ? st : ctx->grp_streams[2 * gi];
+            if (whole) {
+                phase_begin(ctx, ITR_PH_POST_COMBINE, st);
+                // Pass 2 over contiguous ranges of blocks (input order = contiguous rows of the
+                // result): one range normally; several when the result is streamed to the host
+                // (itr_posterior_stream), each followed by an event the copy stream waits for.
+                const int n_ranges = std::max(1, std::min<int>(ctx->stream_ranges, nb));
+                ctx->range_col_end.clear();
+                for (int r = 0; r < n_ranges; ++r) {
+                    const int64_t b0 = (int64_t)nb * r / n_ranges, b1 = (int64_t)nb * (r + 1) / n_ranges;
+                    if (b1 <= b0) continue;
+                    CK(launch_post_tiles(ctx, st, ctx->h_tile_off[b0], ctx->h_tile_off[b1]));
+                    if (ctx->stream_ranges > 0) {
+                        while (ctx->range_events.size() <= ctx->range_col_end.size()) {
+                            cudaEvent_t e = nullptr;
+                            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                            ctx->range_events.push_back(e);
+                        }
+                        CK(cudaEventRecord(ctx->range_events[ctx->range_col_end.size()], st));
+                        ctx->range_col_end.push_back(ctx->h_off[b1]);
+                    }
+                }
+                phase_end(ctx, ITR_PH_POST_COMBINE, st);
+                if (post) {
+                    CK(cudaEventRecord(ecopy, st));
+                    CK(cudaStreamWaitEvent(scopy, ecopy, 0));
+                    CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, scopy));
+                }
+            } else {
+                // pass 2 and download block by block, in the group's forward stream
+                if (gi == 0) phase_begin(ctx, ITR_PH_POST_COMBINE, sf);
+                for (int q = last - 1; q >= first; --q) {
+                    const int32_t blk = ctx->h_order[q];
+                    const int64_t t0 = ctx->h_tile_off[blk], t1 = ctx->h_tile_off[blk + 1];
+                    if (t1 <= t0) continue;
+                    CK(launch_post_tiles(ctx, sf, t0, t1));
+                    if (!post) continue;
+                    CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));
+                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sf); ctx->tr_k.push_back(e); }
+                    CK(cudaStreamWaitEvent(scopy, ctx->grp_events[2 * gi], 0));
+                    const size_t o = (size_t)ctx->h_off[blk] * K, len = (size_t)(ctx->h_off[blk + 1] - ctx->h_off[blk]) * K;
+                    CK(cudaMemcpyAsync(post + o, ctx->d_post + o, len * sizeof(double), cudaMemcpyDeviceToHost, scopy));
+                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, scopy); ctx->tr_c.push_back(e); ctx->tr_b.push_back(blk); }
+                }
+                if (gi == 0) phase_end(ctx, ITR_PH_POST_COMBINE, sf);
+                if (post) {                        // stream2 collects "kernels done" of every group
+                    CK(cudaEventRecord(ctx->grp_events[2 * gi + 1], sf));
+                    CK(cudaStreamWaitEvent(ctx->stream2, ctx->grp_events[2 * gi + 1], 0));
+                }
+                if (!post) {                       // join the group into the copy stream's place: st waits below
+                    CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));
+                    CK(cudaStreamWaitEvent(st, ctx->grp_events[2 * gi], 0));
+                }
+            }
+        }
         CK(cudaGetLastError());
         ctx->have_post = true;
         ctx->post_download = false;
@@ -1295,9 +1352,105 @@ extern "C" int itr_posterior_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_c
 }
 
 // ---------------------------------------------------------------------------------
+// posterior streamed to the host through a bounded ring (chromosome-scale results)
+// ---------------------------------------------------------------------------------
+extern "C" int itr_posterior_stream(itr_ctx *ctx, double *ring, int64_t slot_cols, int n_slots,
+                                    itr_rows_sink sink, void *user) {
+    if (!ctx) return ITR_ERR_ARG;
+    if (!ring || slot_cols < 1 || n_slots < 1)
+        return fail(ctx, ITR_ERR_ARG, "itr_posterior_stream: ring must be non-NULL with slot_cols >= 1 and n_slots >= 1");
+    if (n_slots > 64) n_slots = 64;
+    int rc = need_ready(ctx, "itr_posterior_stream");
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    // Pass 2 in ranges of ~1/16 of the alignment (at least one block each), so that the
+    // first rows leave the device while later ranges are still being computed.
+    const bool was_async = ctx->async;
+    ctx->async = true;
+    ctx->stream_ranges = 16;
+    rc = itr_posterior(ctx, nullptr);
+    ctx->stream_ranges = 0;
+    ctx->async = was_async;
+    if (rc) return rc;
+    const int K = ctx->K;
+    const int64_t n_cols = ctx->n_cols;
+    while ((int)ctx->grp_streams.size() < 2 * 8 + 1) {
+        cudaStream_t s2 = nullptr;
+        cudaEvent_t e2 = nullptr;
+        CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        ctx->grp_streams.push_back(s2);
+        CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        ctx->grp_events.push_back(e2);
+    }
+    cudaStream_t scopy = ctx->grp_streams[16];
+    std::vector<cudaEvent_t> slot_ev(n_slots, nullptr);
+    for (int q = 0; q < n_slots; ++q) CK(cudaEventCreateWithFlags(&slot_ev[q], cudaEventDisableTiming));
+    struct Piece { int64_t col0, n; };
+    std::vector<Piece> inflight(n_slots, Piece{0, 0});
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(scopy);
+        for (cudaEvent_t e : slot_ev)
+            if (e) cudaEventDestroy(e);
+    };
+    // ranges computed by the two-pass path carry events; any other path: the whole result
+    // is complete when the posterior stream is (one wait)
+    const bool ranged = !ctx->range_col_end.empty() && ctx->range_col_end.back() == n_cols;
+    if (!ranged) {
+        CK(cudaEventRecord(ctx->ev_join, ctx->s_post));
+        CK(cudaStreamWaitEvent(scopy, ctx->ev_join, 0));
+    }
+    size_t next_range = 0;
+    int64_t piece = 0;
+    int status = ITR_OK;
+    auto retire = [&](int slot) -> int {          // the copy into `slot` is complete: hand it to the sink
+        if (inflight[slot].n == 0) return 0;
+        if (cudaEventSynchronize(slot_ev[slot]) != cudaSuccess) return fail(ctx, ITR_ERR_CUDA, "itr_posterior_stream: download failed");
+        const Piece pc = inflight[slot];
+        inflight[slot].n = 0;
+        if (sink && sink(user, pc.col0, pc.n, ring + (size_t)slot * slot_cols * K) != 0)
+            return fail(ctx, ITR_ERR_IO, "itr_posterior_stream: the sink asked to stop at column %lld", (long long)pc.col0);
+        return 0;
+    };
+    for (int64_t c0 = 0; c0 < n_cols && status == ITR_OK; ++piece) {
+        // a piece never crosses a range boundary, so it waits for exactly one range
+        int64_t lim = n_cols;
+        if (ranged) {
+            while (ctx->range_col_end[next_range] <= c0) ++next_range;
+            lim = ctx->range_col_end[next_range];
+        }
+        const int64_t n = std::min(slot_cols, lim - c0);
+        const int slot = (int)(piece % n_slots);
+        if ((status = retire(slot)) != ITR_OK) break;
+        if (ranged && cudaStreamWaitEvent(scopy, ctx->range_events[next_range], 0) != cudaSuccess) {
+            status = fail(ctx, ITR_ERR_CUDA, "itr_posterior_stream: cudaStreamWaitEvent failed");
+            break;
+        }
+        if (cudaMemcpyAsync(ring + (size_t)slot * slot_cols * K, ctx->d_post + (size_t)c0 * K, (size_t)n * K * sizeof(double),
+                            cudaMemcpyDeviceToHost, scopy) != cudaSuccess ||
+            cudaEventRecord(slot_ev[slot], scopy) != cudaSuccess) {
+            status = fail(ctx, ITR_ERR_CUDA, "itr_posterior_stream: download failed");
+            break;
+        }
+        inflight[slot] = Piece{c0, n};
+        c0 += n;
+    }
+    for (int q = 0; q < n_slots && status == ITR_OK; ++q) status = retire((int)((piece + q) % n_slots));
+    cleanup();
+    if (status != ITR_OK) return status;
+    CK(cudaStreamSynchronize(ctx->s_post));
+    return ITR_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // posterior CSV straight from the device result (workflow_posterior.py:697-716)
 // ---------------------------------------------------------------------------------
 extern "C" int itr_posterior_write_csv(itr_ctx *ctx, const char *path, const int64_t *positions, int n_threads) {
+    return itr_posterior_write_csv_ex(ctx, path, positions, nullptr, 1, nullptr, n_threads);
+}
+
+extern "C" int itr_posterior_write_csv_ex(itr_ctx *ctx, const char *path, const int64_t *positions,
+                                          const int64_t *block_ids, int write_header, int64_t *block_bytes,
+                                          int n_threads) {
     if (!ctx) return ITR_ERR_ARG;
     if (!path) return fail(ctx, ITR_ERR_ARG, "itr_posterior_write_csv: path is NULL");
     if (!ctx->have_post) return fail(ctx, ITR_ERR_STATE, "itr_posterior_write_csv: no posterior on the device");
@@ -1309,7 +1462,7 @@ extern "C" int itr_posterior_write_csv(itr_ctx *ctx, const char *path, const int
     for (int64_t i = 0; i < nb; ++i) max_len = std::max(max_len, ctx->h_off[i + 1] - ctx->h_off[i]);
     itr::PosteriorCsv w;
     std::string err;
-    if (!w.open(path, K, n_threads, err)) return fail(ctx, ITR_ERR_IO, "itr_posterior_write_csv: %s", err.c_str());
+    if (!w.open(path, K, n_threads, err, write_header != 0)) return fail(ctx, ITR_ERR_IO, "itr_posterior_write_csv: %s", err.c_str());
     double *h[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int rc = ITR_OK;
@@ -1339,8 +1492,10 @@ extern "C" int itr_posterior_write_csv(itr_ctx *ctx, const char *path, const int
         if (cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { rc = fail(ctx, ITR_ERR_CUDA, "itr_posterior_write_csv: download failed"); break; }
         if (i + 1 < nb && fetch(i + 1) != cudaSuccess) { rc = fail(ctx, ITR_ERR_CUDA, "itr_posterior_write_csv: download failed"); break; }
         const int64_t c0 = ctx->h_off[i], n = ctx->h_off[i + 1] - c0;
-        if (!w.write_block(i, positions ? positions + c0 : nullptr, h[i & 1], n, err))
+        const int64_t before = w.bytes_written();
+        if (!w.write_block(block_ids ? block_ids[i] : i, positions ? positions + c0 : nullptr, h[i & 1], n, err))
             rc = fail(ctx, ITR_ERR_IO, "itr_posterior_write_csv: %s", err.c_str());
+        if (block_bytes) block_bytes[i] = w.bytes_written() - before;
     }
     cudaStreamSynchronize(ctx->stream2);
     cleanup();

@@ -79,7 +79,7 @@ static inline char *put_i64(char *p, int64_t v) {
     return r.ptr;
 }
 
-bool PosteriorCsv::open(const char *path, int K, int n_threads, std::string &err) {
+bool PosteriorCsv::open(const char *path, int K, int n_threads, std::string &err, bool header) {
     close();
     fh_ = std::fopen(path, "wb");
     if (!fh_) { err = std::string("cannot open ") + path + " for writing"; return false; }
@@ -90,6 +90,7 @@ bool PosteriorCsv::open(const char *path, int K, int n_threads, std::string &err
     std::string h = "alignment_block_idx,position_idx";
     for (int i = 0; i < K; ++i) h += ",prob_state_" + std::to_string(i);
     h += "\r\n";
+    if (!header) h.clear();
     bytes_ = (int64_t)h.size();
     if (std::fwrite(h.data(), 1, h.size(), fh_) != h.size()) { err = "write failed"; return false; }
     return true;
@@ -174,14 +175,23 @@ extern "C" int itr_csv_format_double(double x, char *out, int cap) {
 
 extern "C" int itr_csv_posterior_host(const char *path, int K, int64_t n_blocks, const int64_t *offsets,
                                       const int64_t *positions, const double *post, int n_threads) {
+    return itr_csv_posterior_host_ex(path, K, n_blocks, offsets, positions, post, nullptr, 1, nullptr, n_threads);
+}
+
+extern "C" int itr_csv_posterior_host_ex(const char *path, int K, int64_t n_blocks, const int64_t *offsets,
+                                         const int64_t *positions, const double *post, const int64_t *block_ids,
+                                         int write_header, int64_t *block_bytes, int n_threads) {
     if (!path || K <= 0 || n_blocks < 0 || (n_blocks > 0 && (!offsets || !post))) return ITR_ERR_ARG;
     itr::PosteriorCsv w;
     std::string err;
-    if (!w.open(path, K, n_threads, err)) return ITR_ERR_IO;
+    if (!w.open(path, K, n_threads, err, write_header != 0)) return ITR_ERR_IO;
     for (int64_t i = 0; i < n_blocks; ++i) {
         const int64_t c0 = offsets[i], n = offsets[i + 1] - c0;
         if (n < 0) return ITR_ERR_ARG;
-        if (!w.write_block(i, positions ? positions + c0 : nullptr, post + (size_t)c0 * K, n, err)) return ITR_ERR_IO;
+        const int64_t before = w.bytes_written();
+        if (!w.write_block(block_ids ? block_ids[i] : i, positions ? positions + c0 : nullptr, post + (size_t)c0 * K, n, err))
+            return ITR_ERR_IO;
+        if (block_bytes) block_bytes[i] = w.bytes_written() - before;
     }
     return w.close() ? ITR_OK : ITR_ERR_IO;
 }

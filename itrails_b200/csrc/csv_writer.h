@@ -16,8 +16,9 @@ int format_repr(double x, char *out);
 class PosteriorCsv {
 public:
     ~PosteriorCsv() { close(); }
-    // Creates/truncates the file and writes the header line for K states.
-    bool open(const char *path, int K, int n_threads, std::string &err);
+    // Creates/truncates the file and writes the header line for K states (header = false:
+    // a part file of a sharded run, spliced behind another file's header later).
+    bool open(const char *path, int K, int n_threads, std::string &err, bool header = true);
     // Appends the rows of one block.  positions == nullptr writes 0..n_rows-1.
     bool write_block(int64_t block_idx, const int64_t *positions, const double *post, int64_t n_rows,
                      std::string &err);

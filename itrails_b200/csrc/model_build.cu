@@ -697,7 +697,13 @@ int ModelBuilder::build(cudaStream_t stream, int n_sets, const double *params, i
         const double N_AB = p[6], N_ABC = p[7], r = p[8];
         for (int q = 0; q < 9; ++q)
             if (!(p[q] > 0.0) || !std::isfinite(p[q])) {
-                msg = "parameter set " + std::to_string(s) + ": every parameter must be positive and finite";
+                static const char *names[9] = {"t_A", "t_B", "t_C", "t_2", "t_upper", "t_out", "N_AB", "N_ABC", "r"};
+                // (t_upper == 0 passes the reference's workflow validation, which only forbids
+                // negative values, but its emission build then divides by the length of the last
+                // interval: ZeroDivisionError in get_emission_prob_mat.py — an error there too)
+                msg = "parameter set " + std::to_string(s) + ": " + names[q] + " = " + std::to_string(p[q]) +
+                      " — every parameter must be positive and finite" +
+                      (q == 4 ? " (t_upper == 0, i.e. t_3 equal to the last ABC cutpoint, is a division by zero in the reference as well)" : "");
                 return ITR_ERR_ARG;
             }
         const double N_ref = N_ABC;

@@ -31,6 +31,7 @@ class Engine:
         self._offsets = None
         self.K = 0
         self.n_sets = 0
+        self._pending = []      # host arrays a deferred call will still write into (alive until sync)
 
     # -- lifetime ----------------------------------------------------------------
     def close(self):
@@ -134,8 +135,13 @@ class Engine:
 
     # -- recursions --------------------------------------------------------------
     def loglik(self, per_block=False):
+        """Summed forward log-likelihood per parameter set (and per block).  In deferred
+        mode (:meth:`set_async`) the returned arrays are filled at :meth:`sync`; the engine
+        keeps them alive until then, so dropping the result cannot leave the library with a
+        dangling pointer."""
         tot = np.empty(self.n_sets)
         pb = np.empty((self.n_sets, self.n_blocks)) if per_block else None
+        self._pending = [tot, pb]       # (a second deferred loglik completes the first one inside the library)
         self._ck(self._lib.itr_loglik(self._ctx, L.as_ptr(tot, ctypes.c_double),
                                       L.as_ptr(pb, ctypes.c_double)))
         return (tot, pb) if per_block else tot
@@ -170,16 +176,53 @@ class Engine:
         self._ck(self._lib.itr_posterior_fetch_range(self._ctx, c0, n, L.as_ptr(out, ctypes.c_double)))
         return out
 
-    def write_posterior_csv(self, path, positions=None, n_threads=0):
+    def write_posterior_csv(self, path, positions=None, n_threads=0, block_ids=None, header=True):
         """``{prefix}.posterior.csv`` (workflow_posterior.py:697-716) written by the native
         writer straight from the posterior kept on the device; ``positions`` = one int64
-        per column (reference coordinates) or None for 0..T-1 within each block."""
+        per column (reference coordinates) or None for 0..T-1 within each block.
+        ``block_ids`` (one per loaded block) replaces the printed block index and
+        ``header=False`` leaves the header out: the part file of one rank of a sharded
+        run.  Returns the bytes written per block."""
         if positions is not None:
             positions = np.ascontiguousarray(positions, dtype=np.int64)
             if positions.shape != (self.n_columns,):
                 raise ValueError("positions must hold one entry per alignment column")
-        self._ck(self._lib.itr_posterior_write_csv(self._ctx, os.fsencode(path),
-                                                   L.as_ptr(positions, ctypes.c_int64), int(n_threads)))
+        if block_ids is not None:
+            block_ids = np.ascontiguousarray(block_ids, dtype=np.int64)
+            if block_ids.shape != (self.n_blocks,):
+                raise ValueError("block_ids must hold one entry per loaded block")
+        nbytes = np.zeros(self.n_blocks, dtype=np.int64)
+        self._ck(self._lib.itr_posterior_write_csv_ex(
+            self._ctx, os.fsencode(path), L.as_ptr(positions, ctypes.c_int64), L.as_ptr(block_ids, ctypes.c_int64),
+            1 if header else 0, L.as_ptr(nbytes, ctypes.c_int64), int(n_threads)))
+        return nbytes
+
+    def posterior_stream(self, ring, slot_cols, n_slots, sink=None):
+        """Posterior decoding streamed through a bounded host ring (itr_posterior_stream):
+        ``ring`` is a C-contiguous float64 array of at least n_slots * slot_cols * K values
+        (page-locked for full PCIe speed); ``sink(col0, rows)`` — optional — receives every
+        piece as an (n, K) view into the ring, in ascending column order, and must be done
+        with it when it returns.  The full result also stays on the device."""
+        ring = np.asarray(ring)
+        if ring.dtype != np.float64 or not ring.flags.c_contiguous or ring.size < n_slots * slot_cols * self.K:
+            raise ValueError("ring must be a C-contiguous float64 array of n_slots * slot_cols * K values")
+        K = self.K
+        err = []
+        cb = None
+        if sink is not None:
+            def _cb(_user, col0, n, rows):
+                try:
+                    sink(int(col0), np.ctypeslib.as_array(rows, shape=(int(n), K)))
+                    return 0
+                except BaseException as e:      # noqa: BLE001 - must not unwind through the C frame
+                    err.append(e)
+                    return 1
+            cb = L.ROWS_SINK(_cb)
+        rc = self._lib.itr_posterior_stream(self._ctx, L.as_ptr(ring, ctypes.c_double), int(slot_cols), int(n_slots),
+                                            ctypes.cast(cb, ctypes.c_void_p) if cb is not None else None, None)
+        if err:
+            raise err[0]
+        self._ck(rc)
 
     def viterbi_block(self, i, out=None):
         """uint8 state path of block ``i`` from the result kept on the device."""
@@ -204,6 +247,7 @@ class Engine:
 
     def sync(self):
         self._ck(self._lib.itr_sync(self._ctx))
+        self._pending = []
 
     # -- introspection -----------------------------------------------------------
     def phase_ms(self, name):

@@ -7,9 +7,12 @@ reference's optimizer.py, with the numerics on the GPU:
     optimization_wrapper / optimizer      optimizer.py:396-637
     write_list                            optimizer.py:380-393
 
-Under ``torch.distributed`` (one process per GPU) the log-likelihood wrappers shard
-the blocks over ranks and all-reduce the scalar; the decoders return this rank's
-blocks only (see ``itrails_b200.distributed``).
+With more than one GPU (one process per GPU under ``torch.distributed``, and / or
+several GPUs driven by this process — ``itrails_b200.ngpu``) the blocks are
+LPT-partitioned over the GPUs; the log-likelihood wrappers all-reduce the scalar, and
+the decoders gather their results so that EVERY wrapper returns one entry per ``V_lst``
+block in input order on every rank, exactly like the single-GPU call
+(``itrails_b200.distributed``).
 """
 from __future__ import annotations
 
@@ -19,8 +22,9 @@ import time
 import numpy as np
 
 from . import distributed as dist_
+from . import ngpu
 from .cutpoints import cutpoints_ABC
-from .engine_cache import ensure_blocks, get_engine
+from .engine_cache import ensure_blocks, get_engine  # noqa: F401  (get_engine: re-exported for callers)
 from .read_data import order_lists
 from .yaml_helpers import update_best_model
 
@@ -48,45 +52,131 @@ def viterbi_tables(a, b, pi, V_lst):
     with np.errstate(divide="ignore"):
         log_a = np.log(np.asarray(a, dtype=np.float64))
         log_E = np.log(E)
-        first = np.array([int(V[0]) for V in V_lst])
+        first = np.array([int(V[0]) for V in V_lst], dtype=np.int64)
         omega0 = np.log(pi[None, :] * E[:, first].T)
     return log_a, log_E, np.ascontiguousarray(omega0)
 
 
 # ---------------------------------------------------------------------------
+# sharding: which blocks live on which GPU, and putting results back in input order
+# ---------------------------------------------------------------------------
+class _Shard:
+    """One GPU's share of ``V_lst``: ``ids`` are the global block indices (ascending)."""
+    __slots__ = ("device", "local", "ids", "eng")
+
+    def __init__(self, device, local, ids):
+        self.device, self.local, self.ids, self.eng = device, local, ids, None
+
+
+class _Plan:
+    __slots__ = ("V_lst", "shards", "parts", "lengths", "n_local", "world", "rank")
+
+
+_PLAN_CACHE = {}
+
+
+def _plan(V_lst):
+    """LPT partition of ``V_lst`` over every GPU of the job (cached per list object), with
+    this process's shares resident in HBM."""
+    hit = _PLAN_CACHE.get(id(V_lst))
+    if hit is not None and hit.V_lst is V_lst and len(hit.lengths) == len(V_lst):
+        plan = hit
+    else:
+        _PLAN_CACHE.clear()
+        plan = _Plan()
+        plan.V_lst = V_lst
+        plan.rank, plan.world = dist_.rank_world()
+        devices = ngpu.local_devices()
+        plan.n_local = len(devices)
+        plan.lengths = np.array([len(v) for v in V_lst], dtype=np.int64)
+        n_parts = plan.world * plan.n_local
+        if n_parts == 1:
+            plan.parts = [np.arange(len(V_lst), dtype=np.int64)]
+            plan.shards = [_Shard(devices[0], V_lst, plan.parts[0])]
+        else:
+            plan.parts = dist_.lpt_partition(plan.lengths, n_parts)
+            plan.shards = []
+            for g, dev in enumerate(devices):
+                ids = plan.parts[plan.rank * plan.n_local + g]
+                plan.shards.append(_Shard(dev, [V_lst[i] for i in ids], ids))
+        _PLAN_CACHE[id(V_lst)] = plan
+    for sh in plan.shards:              # (an empty share is legal: fewer blocks than GPUs)
+        sh.eng = ensure_blocks(sh.local, sh.device) if len(sh.ids) else None
+    return plan
+
+
+def _each(plan, fn):
+    """fn(shard) for every non-empty local shard; concurrently when this process drives
+    several GPUs (the C ABI calls release the GIL).  Returns results in shard order
+    (None for empty shards)."""
+    live = [sh for sh in plan.shards if sh.eng is not None]
+    if len(live) <= 1:
+        res = {id(sh): fn(sh) for sh in live}
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(live)) as pool:
+            res = dict(zip((id(sh) for sh in live), pool.map(fn, live)))
+    return [res.get(id(sh)) for sh in plan.shards]
+
+
+def _global_order(plan, local_flat, dtype, trailing=()):
+    """Per-shard flat results (columns of the shard's blocks back to back, None for empty
+    shards) -> list with one array per block of ``V_lst`` in input order, on every rank."""
+    n = len(plan.lengths)
+    if plan.world * plan.n_local == 1:
+        off = np.concatenate([[0], np.cumsum(plan.lengths)])
+        flat = local_flat[0]
+        return [flat[off[i]:off[i + 1]] for i in range(n)]
+    mine = [f if f is not None else np.empty((0,) + tuple(trailing), dtype=dtype) for f in local_flat]
+    per_rank = [mine]
+    if plan.world > 1:
+        # one contribution per rank: its shards' results back to back
+        counts = [int(sum(plan.lengths[plan.parts[r * plan.n_local + g]].sum() for g in range(plan.n_local)))
+                  for r in range(plan.world)]
+        cat = np.concatenate(mine) if len(mine) > 1 else mine[0]
+        gathered = dist_.allgather_ragged(cat, counts)
+        per_rank = []
+        for r in range(plan.world):
+            cuts = np.cumsum([int(plan.lengths[plan.parts[r * plan.n_local + g]].sum()) for g in range(plan.n_local)])[:-1]
+            per_rank.append(np.split(gathered[r], cuts) if plan.n_local > 1 else [gathered[r]])
+    out = [None] * n
+    for r, shards in enumerate(per_rank):
+        for g, flat in enumerate(shards):
+            ids = plan.parts[(r if plan.world > 1 else plan.rank) * plan.n_local + g]
+            off = np.concatenate([[0], np.cumsum(plan.lengths[ids])])
+            for k, i in enumerate(ids):
+                out[int(i)] = flat[off[k]:off[k + 1]]
+    return out
+
+
+def _sum_loglik(plan, partials):
+    """Sum of per-shard log-likelihood vectors over local shards, then over ranks."""
+    vecs = [p for p in partials if p is not None]
+    n_sets = len(vecs[0]) if vecs else None
+    if plan.world > 1 and any(len(p) == 0 for p in plan.parts):
+        # fewer blocks than GPUs: a rank without blocks still takes part in the all-reduce,
+        # with the vector length the others use (every rank sees the same partition, so
+        # either all of them make this extra exchange or none does)
+        n_sets = int(dist_.allreduce_max(-1 if n_sets is None else n_sets))
+    total = np.sum(vecs, axis=0) if vecs else np.zeros(n_sets)
+    if plan.world > 1:
+        dev = plan.shards[0].device
+        total = dist_.allreduce_sum(total, dev)
+    return np.asarray(total, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------
 # wrappers
 # ---------------------------------------------------------------------------
-def _local(V_lst):
-    if dist_.is_active():
-        local, ids = dist_.shard_blocks(V_lst)
-        return local, ids
-    return V_lst, None
-
-
-_SHARD_CACHE = {}
-
-
-def _resident(V_lst):
-    """Engine with this rank's share of V_lst resident in HBM."""
-    if not dist_.is_active():
-        return ensure_blocks(V_lst), V_lst
-    key = id(V_lst)
-    hit = _SHARD_CACHE.get(key)
-    if hit is None or hit[0] is not V_lst:
-        _SHARD_CACHE.clear()
-        local, ids = dist_.shard_blocks(V_lst)
-        _SHARD_CACHE[key] = (V_lst, local, ids)
-        hit = _SHARD_CACHE[key]
-    return ensure_blocks(hit[1]), hit[1]
-
-
 def loglik_wrapper(a, b, pi, V_lst):
     """Sum over blocks of the forward log-likelihood (optimizer.py:93-116)."""
-    eng, _ = _resident(V_lst)
-    eng.set_model(a, b, pi)
-    total = eng.loglik()
-    if dist_.is_active():
-        total = dist_.allreduce_sum(total, eng.device)
+    plan = _plan(V_lst)
+
+    def one(sh):
+        sh.eng.set_model(a, b, pi)
+        return sh.eng.loglik()
+
+    total = _sum_loglik(plan, _each(plan, one))
     return float(total[0])      # a Python float, as the reference's numba forward_loglik returns
 
 
@@ -97,37 +187,105 @@ def loglik_wrapper_par(a, b, pi, V_lst):
 
 
 def post_prob_wrapper(a, b, pi, V_lst):
-    """List of (T, K) float64 posterior matrices, one per block (optimizer.py:241-262)."""
-    eng, local = _resident(V_lst)
-    eng.set_model(a, b, pi)
-    post = eng.posterior()
-    return eng.split(post)
+    """List of (T, K) float64 posterior matrices, one per block of ``V_lst`` in input
+    order (optimizer.py:241-262).  On several GPUs every rank receives the full list
+    (the shards are exchanged after decoding); for results that do not fit in host
+    memory use ``post_prob_to_csv``."""
+    plan = _plan(V_lst)
+    K = np.asarray(a).shape[0]
+
+    def one(sh):
+        sh.eng.set_model(a, b, pi)
+        return sh.eng.posterior()
+
+    return _global_order(plan, _each(plan, one), np.float64, trailing=(K,))
+
+
+def _csv_header(K):
+    return ("alignment_block_idx,position_idx" + "".join(f",prob_state_{i}" for i in range(K)) + "\r\n").encode()
 
 
 def post_prob_to_csv(a, b, pi, V_lst, output_file, ref_coordinates=None, n_threads=0):
     """Posterior decoding written straight to ``output_file`` in the reference's format
     (workflow_posterior.py:697-716) without materialising the list of (T, K) matrices on
     the host: the result stays in HBM and the native writer streams it block by block.
-    Byte-identical to ``csv.writer`` over ``post_prob_wrapper``'s result."""
-    eng, local = _resident(V_lst)
-    eng.set_model(a, b, pi)
-    positions = None
-    if ref_coordinates is not None:
-        if [len(c) for c in ref_coordinates] != [len(v) for v in local]:
-            raise IndexError("reference coordinates do not match the alignment blocks")
-        positions = np.concatenate([np.asarray(c, dtype=np.int64) for c in ref_coordinates])
-    eng.posterior(fetch=False)
-    eng.write_posterior_csv(output_file, positions, n_threads)
+    Byte-identical to ``csv.writer`` over ``post_prob_wrapper``'s result.  On several
+    GPUs every GPU writes the rows of its own blocks — with their GLOBAL block index and
+    coordinates — to a part file, and rank 0 splices the parts in input block order."""
+    plan = _plan(V_lst)
+    if ref_coordinates is not None and [len(c) for c in ref_coordinates] != [int(n) for n in plan.lengths]:
+        raise IndexError("reference coordinates do not match the alignment blocks")
+    single = plan.world * plan.n_local == 1
+
+    def positions_of(ids):
+        if ref_coordinates is None:
+            return None
+        return np.concatenate([np.asarray(ref_coordinates[int(i)], dtype=np.int64) for i in ids])
+
+    def one(sh):
+        sh.eng.set_model(a, b, pi)
+        sh.eng.posterior(fetch=False)
+        if single:
+            sh.eng.write_posterior_csv(output_file, positions_of(sh.ids), n_threads)
+            return None
+        part = f"{output_file}.part{plan.rank * plan.n_local + plan.shards.index(sh)}"
+        return part, sh.eng.write_posterior_csv(part, positions_of(sh.ids), n_threads, block_ids=sh.ids, header=False)
+
+    res = _each(plan, one)
+    if single:
+        return
+    # (part file, bytes per block) of every part of the job, in part order
+    mine = [(r[0], r[1].tolist()) if r is not None else (None, []) for r in res]
+    parts_info = [x for per_rank in dist_.allgather_object(mine) for x in per_rank]
+    if plan.rank == 0:
+        K = np.asarray(a).shape[0]
+        handles = [open(pth, "rb") if pth else None for pth, _ in parts_info]
+        cursor = [0] * len(parts_info)          # next block of each part (parts hold ascending ids)
+        owner = np.empty(len(plan.lengths), dtype=np.int64)
+        for q, ids in enumerate(plan.parts):
+            owner[ids] = q
+        with open(output_file, "wb") as out:
+            out.write(_csv_header(K))
+            for i in range(len(plan.lengths)):
+                q = int(owner[i])
+                left = parts_info[q][1][cursor[q]]
+                cursor[q] += 1
+                while left > 0:
+                    buf = handles[q].read(min(left, 1 << 24))
+                    if not buf:
+                        raise OSError(f"part file {parts_info[q][0]} is shorter than its index")
+                    out.write(buf)
+                    left -= len(buf)
+        for h, (pth, _) in zip(handles, parts_info):
+            if h is not None:
+                h.close()
+                os.remove(pth)
+    dist_.barrier()
 
 
 def viterbi_wrapper(a, b, pi, V_lst):
-    """List of float64 state paths, one per block (optimizer.py:357-377; the reference
-    returns float arrays, e.g. ``14.0``)."""
-    eng, local = _resident(V_lst)
-    eng.set_model(a, b, pi)
-    log_a, log_E, omega0 = viterbi_tables(a, b, pi, local)
-    path = eng.viterbi(log_a, log_E, omega0)
-    return [p.astype(np.float64) for p in eng.split(path)]
+    """List of float64 state paths, one per block of ``V_lst`` in input order
+    (optimizer.py:357-377; the reference returns float arrays, e.g. ``14.0``)."""
+    plan = _plan(V_lst)
+
+    def one(sh):
+        sh.eng.set_model(a, b, pi)
+        return sh.eng.viterbi(*viterbi_tables(a, b, pi, sh.local))
+
+    return [p.astype(np.float64) for p in _global_order(plan, _each(plan, one), np.uint8)]
+
+
+def _objective_batch(rows, n_int_AB, n_int_ABC, V_lst):
+    """Summed log-likelihood of every parameter row: batched model build + multi-set
+    forward sweep on every GPU's share, then the scalar reduction."""
+    plan = _plan(V_lst)
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+
+    def one(sh):
+        sh.eng.build_model(rows, n_int_AB, n_int_ABC, fetch=False)
+        return sh.eng.loglik()
+
+    return _sum_loglik(plan, _each(plan, one))
 
 
 # ---------------------------------------------------------------------------
@@ -184,11 +342,7 @@ def optimization_wrapper(arg_lst, optimized_params, case, d, V_lst, res_name, in
     # trans_emiss_calc + loglik_wrapper of the reference (optimizer.py:543-567), without the
     # round trip of (a, b, pi) through the host: the builder leaves the model installed on
     # the device next to this rank's resident blocks.
-    eng, _ = _resident(V_lst)
-    eng.build_model(np.array([model_args(d_copy)]), d_copy["n_int_AB"], d_copy["n_int_ABC"], fetch=False)
-    total = eng.loglik()
-    if dist_.is_active():
-        total = dist_.allreduce_sum(total, eng.device)
+    total = _objective_batch(np.array([model_args(d_copy)]), d_copy["n_int_AB"], d_copy["n_int_ABC"], V_lst)
     loglik = float(total[0])
     rank, _world = dist_.rank_world()
     if rank == 0:
@@ -217,12 +371,7 @@ def loglik_sweep(arg_sets, optimized_params, case, d, V_lst):
             d_copy[param] = float(args[i])
         derive_times(d_copy, case)
         rows.append(model_args(d_copy))
-    eng, _ = _resident(V_lst)
-    eng.build_model(np.array(rows, dtype=np.float64), d["n_int_AB"], d["n_int_ABC"], fetch=False)
-    total = eng.loglik()
-    if dist_.is_active():
-        total = dist_.allreduce_sum(total, eng.device)
-    return np.asarray(total, dtype=np.float64)
+    return _objective_batch(np.array(rows, dtype=np.float64), d["n_int_AB"], d["n_int_ABC"], V_lst)
 
 
 def _optimizer_batched(optim_variables, optim_list, bounds, d, V_lst, res_name, case):

@@ -27,7 +27,7 @@ import yaml
 
 from . import __version__
 from .cutpoints import cutpoints_AB, cutpoints_ABC
-from .ngpu import update_n_cpu
+from .ngpu import update_n_cpu, update_n_gpu
 from .yaml_helpers import FlowSeq, load_config
 
 TIME_CASES = {
@@ -176,6 +176,8 @@ def optimize_main(argv=None):
     os.makedirs(output_dir or ".", exist_ok=True)
     print(f"Results will be saved to: {output_dir}.")
     settings["n_cpu"] = update_n_cpu(settings.get("n_cpu"))
+    if settings.get("n_gpu") is not None:        # (this package's addition: GPUs driven by this process)
+        update_n_gpu(settings.get("n_gpu"))
     settings["output_prefix"], settings["input_maf"] = user_output, maf_path
     mu = float(config["fixed_parameters"]["mu"])
     method = str(settings["method"]).lower()
@@ -234,6 +236,7 @@ def _decode_parser(what):
     for name in ("mu", "t1", "t_A", "t_B", "t_C", "t2", "t3", "t_upper", "t_out", "N_AB", "N_ABC", "r"):
         p.add_argument(f"--{name}", type=float)
     p.add_argument("--n_cpu", type=int)
+    p.add_argument("--n_gpu", type=int, help="GPUs this process drives (blocks are sharded over them); default 1")
     p.add_argument("--species_list", nargs="+")
     p.add_argument("--reference", type=str)
     p.add_argument("--n_int_AB", type=int)
@@ -420,7 +423,7 @@ def _decode_main(what, argv):
         if v is not None:
             config["optimized_parameters"].pop(p, None)
             config["fixed_parameters"][p] = v
-    for key in ("n_cpu", "species_list", "reference", "n_int_AB", "n_int_ABC", "cutpoints_AB", "cutpoints_ABC"):
+    for key in ("n_cpu", "n_gpu", "species_list", "reference", "n_int_AB", "n_int_ABC", "cutpoints_AB", "cutpoints_ABC"):
         if getattr(args, key) is not None:
             config["settings"][key] = getattr(args, key)
     settings = config["settings"]
@@ -430,6 +433,8 @@ def _decode_main(what, argv):
     os.makedirs(output_dir or ".", exist_ok=True)
     print(f"Results will be saved to: {output_dir} as '{output_prefix}.{what}.csv'.")
     update_n_cpu(settings.get("n_cpu"))
+    if settings.get("n_gpu") is not None:
+        update_n_gpu(settings.get("n_gpu"))
     if "species_list" not in settings or len(settings["species_list"]) != 4:
         raise ValueError("Error: species_list must name four species.")
     species_list = list(settings["species_list"])
@@ -458,18 +463,25 @@ def _decode_main(what, argv):
         fixed_dict["t_out"], fixed_dict["N_AB"], fixed_dict["N_ABC"], fixed_dict["r"],
         fixed_dict["n_int_AB"], fixed_dict["n_int_ABC"], norm_cut_AB, norm_cut_ABC)
 
+    # Several GPUs: every process decodes its share of the blocks, the wrappers return the
+    # whole result in input order, and rank 0 alone writes the files.
+    from . import distributed as dist_
+    writer = dist_.rank_world()[0] == 0
     hidden_file = os.path.join(output_dir, f"{output_prefix}.hidden_states.csv")
-    if os.path.exists(hidden_file):
-        print(f"Warning: File '{hidden_file}' already exists.")
-        hidden_file = os.path.join(output_dir, f"{output_prefix}.hidden_states_2.csv")
-        print(f"Using an alternative file name: {hidden_file}")
-    write_hidden_states(hidden_file, hidden_names, abs_cut_ABC)
-    print(f"Hidden states written to file {hidden_file}.")
+    if writer:
+        if os.path.exists(hidden_file):
+            print(f"Warning: File '{hidden_file}' already exists.")
+            hidden_file = os.path.join(output_dir, f"{output_prefix}.hidden_states_2.csv")
+            print(f"Using an alternative file name: {hidden_file}")
+        write_hidden_states(hidden_file, hidden_names, abs_cut_ABC)
+        print(f"Hidden states written to file {hidden_file}.")
 
     output_file = os.path.join(output_dir, f"{output_prefix}.{what}.csv")
     if what == "viterbi":
         print("Running viterbi.")
         result = viterbi_wrapper(a=a, b=b, pi=pi, V_lst=maf_alignment)
+        if not writer:
+            return output_file
         print("Writing results to file.")
         with open(output_file, "w", newline="") as fh:
             w = csv.writer(fh)
@@ -481,8 +493,7 @@ def _decode_main(what, argv):
         print(f"Viterbi decoding complete. Results saved to {output_file}.")
     else:
         print("Running posterior decoding.")
-        from . import distributed as dist_
-        native = not dist_.is_active() and os.environ.get("ITRAILS_PY_CSV") is None and (
+        native = os.environ.get("ITRAILS_PY_CSV") is None and (
             ref_coordinates is None or [len(c) for c in ref_coordinates] == [len(v) for v in maf_alignment])
         if native:
             print("Writing results to file.")
@@ -490,6 +501,8 @@ def _decode_main(what, argv):
             print(f"Posterior decoding complete. Results saved to {output_file}.")
             return output_file
         result = post_prob_wrapper(a=a, b=b, pi=pi, V_lst=maf_alignment)
+        if not writer:
+            return output_file
         print("Writing results to file.")
         with open(output_file, "w", newline="") as fh:
             w = csv.writer(fh)

@@ -378,37 +378,33 @@ def test_write_maf_roundtrip(tmp_path):
     assert len(co[1]) == 50
 
 
+def _torchrun(script, port, nproc=2, env=None, timeout=600):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                          capture_output=True, text=True, timeout=timeout, env=e)
+
+
 def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
     """The reference-style wrappers under torch.distributed (gloo, 2 ranks, CPU): every
     rank loads only its LPT share of the blocks, the log-likelihood is all-reduced to the
-    full sum, the decoders return the rank's own blocks, and only rank 0 writes the
-    optimiser's files.  The GPU engine is replaced by a stand-in that answers with the
-    oracle, so this covers the host logic of the N > 1 path."""
+    full sum, the decoders return ONE RESULT PER BLOCK OF V_lst IN INPUT ORDER on every
+    rank (the reference's contract, optimizer.py:241-262, 357-377), a rank whose share is
+    empty (fewer blocks than ranks) neither crashes nor hangs the all-reduce, and only
+    rank 0 writes the optimiser's files.  The GPU engine is replaced by a stand-in that
+    answers with the oracle (tests/fake_engine.py), so this covers the host logic of the
+    N > 1 path."""
     script = tmp_path / "w2.py"
     script.write_text(textwrap.dedent(f"""
         import os, sys
-        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "oracle"))
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "oracle")); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
         import numpy as np, torch.distributed as dist, yaml
-        import hmm_oracle as ho, ctmc_oracle as co
-        from itrails_b200 import distributed as D, engine_cache, optimizer as opt_mod
+        import hmm_oracle as ho
+        from fake_engine import FakeEngine
+        from itrails_b200 import distributed as D, engine_cache
         import itrails_b200.optimizer as O
-
-        class FakeEngine:
-            device = 0
-            def load_blocks(self, V_lst): self.V = list(V_lst); self.loads = getattr(self, "loads", 0) + 1
-            def set_model(self, a, b, pi): self.m = (a, b, pi)
-            def build_model(self, params, n_ab, n_abc, cut_AB=None, cut_ABC=None, fetch=True):
-                self.sets = [co.trans_emiss_calc(*row, n_ab, n_abc)[:3] for row in params]
-                self.m = self.sets[0]
-                return None, None, None, None
-            def loglik(self):
-                sets = getattr(self, "sets", None) or [self.m]
-                return np.array([ho.loglik_wrapper(*m, self.V) for m in sets])
-            def viterbi(self, log_a, log_E, omega0):
-                return np.concatenate([p for p in ho.viterbi_wrapper(*self.m, self.V)]).astype(np.uint8)
-            def split(self, flat):
-                off = np.cumsum([0] + [len(v) for v in self.V]); return [flat[off[i]:off[i + 1]] for i in range(len(self.V))]
-        engine_cache._ENGINE = FakeEngine()
+        engine_cache._ENGINE = FakeEngine(int(os.environ["LOCAL_RANK"]))
 
         dist.init_process_group("gloo")
         rank = dist.get_rank()
@@ -423,9 +419,23 @@ def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
         assert engine_cache._ENGINE.loads == 1 and ll2 == ll
         mine = D.lpt_partition([len(v) for v in V_lst], 2)[rank]
         assert [len(v) for v in engine_cache._ENGINE.V] == [len(V_lst[i]) for i in mine]
+        # decoders: the full result, in input order, on both ranks
         paths = O.viterbi_wrapper(a, b, pi, V_lst)
         ref = ho.viterbi_wrapper(a, b, pi, V_lst)
-        assert len(paths) == len(mine) and all(np.array_equal(p, ref[i]) for p, i in zip(paths, mine))
+        assert len(paths) == len(V_lst) and all(p.dtype == np.float64 and np.array_equal(p, r) for p, r in zip(paths, ref))
+        post = O.post_prob_wrapper(a, b, pi, V_lst)
+        refp = ho.post_prob_wrapper(a, b, pi, V_lst)
+        assert len(post) == len(V_lst) and all(p.shape == r.shape and np.array_equal(p, r) for p, r in zip(post, refp))
+        # fewer blocks than ranks: rank 1's share is empty
+        one = [V_lst[3]]
+        assert len(D.lpt_partition([len(one[0])], 2)[1]) == 0
+        ll1 = O.loglik_wrapper(a, b, pi, one)
+        w1 = ho.loglik_wrapper(a, b, pi, one)
+        assert abs(ll1 - w1) <= 1e-12 * abs(w1)
+        p1 = O.viterbi_wrapper(a, b, pi, one)
+        assert len(p1) == 1 and np.array_equal(p1[0], ref[3])
+        q1 = O.post_prob_wrapper(a, b, pi, one)
+        assert len(q1) == 1 and np.array_equal(q1[0], refp[3])
         # objective: rank 0 alone writes the history / best-model files
         d = dict(zip(("t_A", "t_B", "t_C", "t_2", "t_upper", "t_out", "N_AB", "N_ABC", "r"), g["args"]))
         d.update(n_int_AB=1, n_int_ABC=1)
@@ -437,10 +447,12 @@ def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
         dist.barrier()
         val = O.optimization_wrapper([d["N_AB"]], ["N_AB"], frozenset(["t_A", "t_B", "t_C"]), d, V_lst, res, {{"Nfeval": 0, "time": 0.0}})
         assert abs(-val - want) <= 1e-9 * abs(want), (val, want)
+        v1 = O.optimization_wrapper([d["N_AB"]], ["N_AB"], frozenset(["t_A", "t_B", "t_C"]), d, one, res, {{"Nfeval": 1, "time": 0.0}})
+        assert abs(-v1 - w1) <= 1e-9 * abs(w1), (v1, w1)
         dist.barrier()
         if rank == 0:
             lines = open(res + ".optimization_history.csv").read().strip().splitlines()
-            assert len(lines) == 1 and lines[0].startswith("0,")
+            assert len(lines) == 2 and lines[0].startswith("0,") and lines[1].startswith("1,")
         # batched simplex on the sharded objective: every rank walks the same simplex (the
         # all-reduced values are identical), rank 0 alone writes the files; same evaluations
         # as the sequential search
@@ -467,11 +479,69 @@ def test_gloo_world_size_2_wrappers_shard_and_reduce(tmp_path):
             assert abs(best["results"]["log_likelihood"] + rb.fun) <= 1e-12 * abs(rb.fun)
         print("rank", rank, "ok")
     """))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
-                       capture_output=True, text=True, timeout=600)
+    r = _torchrun(script, 29613)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_sharded_decode_clis_write_the_single_gpu_files(tmp_path):
+    """itrails-viterbi / itrails-posterior with the blocks sharded over GPUs must write the
+    files a single GPU writes (workflow_viterbi.py:688-743, workflow_posterior.py:693-716:
+    global block indices, reference coordinates of the right block, one writer): run the
+    CLIs (a) in one process on one engine, (b) under torchrun with 2 gloo ranks, (c) in one
+    process driving two engines (``--n_gpu 2``), and compare the CSVs byte for byte — the
+    posterior both through the native part-file writer and through the csv.writer loop."""
+    from itrails_b200 import synth
+    m = golden("model_2_2_example.npz")
+    rng = np.random.default_rng(12)
+    V_lst = [ho.sample_block(m["a"], m["b"], m["pi"], int(T), rng, p_n=0.05) for T in (300, 41, 1, 222, 97, 160, 35)]
+    species = ["hg38", "panTro5", "gorGor5", "ponAbe2"]
+    maf = tmp_path / "s.maf"
+    synth.write_maf(str(maf), V_lst, species)
+    script = tmp_path / "cli.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "oracle")); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        from fake_engine import FakeEngine
+        from itrails_b200 import engine_cache, workflows
+        import itrails_b200.engine_cache as ec
+        ec.Engine = FakeEngine                      # every engine the package creates is the stand-in
+        mode, out = sys.argv[1], sys.argv[2]
+        extra = []
+        if mode == "torchrun":
+            import torch.distributed as dist
+            dist.init_process_group("gloo")
+        elif mode == "ngpu2":
+            extra = ["--n_gpu", "2"]
+        common = ["--input", {str(maf)!r}, "--mu", "1e-8", "--t1", "240000", "--t2", "40000", "--t_upper", "745069.3855",
+                  "--N_AB", "50000", "--N_ABC", "50000", "--r", "1e-8", "--n_int_AB", "2", "--n_int_ABC", "2",
+                  "--species_list", *{species!r}, "--reference", "hg38"] + extra
+        workflows.viterbi_main(common + ["--output", os.path.join(out, "v")])
+        workflows.posterior_main(common + ["--output", os.path.join(out, "p")])
+        os.environ["ITRAILS_PY_CSV"] = "1"
+        workflows.posterior_main(common + ["--output", os.path.join(out, "q")])
+        print("done")
+    """))
+    outs = {}
+    for mode in ("single", "torchrun", "ngpu2"):
+        out = tmp_path / mode
+        out.mkdir()
+        if mode == "torchrun":
+            r = _torchrun(f"{script} torchrun {out}".split()[0], 29617) if False else subprocess.run(
+                [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                 "--master-port", "29617", str(script), "torchrun", str(out)], capture_output=True, text=True, timeout=600)
+        else:
+            env = {k: v for k, v in os.environ.items() if k not in ("LOCAL_RANK", "RANK", "WORLD_SIZE", "ITRAILS_DEVICE")}
+            r = subprocess.run([sys.executable, str(script), mode, str(out)], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, mode + r.stdout[-3000:] + r.stderr[-3000:]
+        outs[mode] = {f: open(out / f, "rb").read() for f in ("v.viterbi.csv", "p.posterior.csv", "q.posterior.csv")}
+        assert not [f for f in os.listdir(out) if ".part" in f], "part files must be removed after the splice"
+    single = outs["single"]
+    assert single["p.posterior.csv"] == single["q.posterior.csv"]
+    assert single["v.viterbi.csv"].count(b"\n") > 12 and single["p.posterior.csv"].count(b"\n") == 1 + sum(len(v) for v in V_lst)
+    for mode in ("torchrun", "ngpu2"):
+        for f, data in outs[mode].items():
+            assert data == single[f], f"{mode}: {f} differs from the single-GPU file"
 
 
 def test_native_posterior_csv_is_byte_identical_to_csv_writer(tmp_path):
