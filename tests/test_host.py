@@ -494,7 +494,7 @@ def test_sharded_decode_clis_write_the_single_gpu_files(tmp_path):
     from itrails_b200 import synth
     m = golden("model_2_2_example.npz")
     rng = np.random.default_rng(12)
-    V_lst = [ho.sample_block(m["a"], m["b"], m["pi"], int(T), rng, p_n=0.05) for T in (300, 41, 1, 222, 97, 160, 35)]
+    V_lst = [ho.sample_block(m["a"], m["b"], m["pi"], int(T), rng, p_n=0.05) for T in (3000, 410, 1, 2220, 970, 1600, 350)]
     species = ["hg38", "panTro5", "gorGor5", "ponAbe2"]
     maf = tmp_path / "s.maf"
     synth.write_maf(str(maf), V_lst, species)
@@ -538,7 +538,7 @@ def test_sharded_decode_clis_write_the_single_gpu_files(tmp_path):
         assert not [f for f in os.listdir(out) if ".part" in f], "part files must be removed after the splice"
     single = outs["single"]
     assert single["p.posterior.csv"] == single["q.posterior.csv"]
-    assert single["v.viterbi.csv"].count(b"\n") > 12 and single["p.posterior.csv"].count(b"\n") == 1 + sum(len(v) for v in V_lst)
+    assert single["v.viterbi.csv"].count(b"\n") >= 8 and single["p.posterior.csv"].count(b"\n") == 1 + sum(len(v) for v in V_lst)
     for mode in ("torchrun", "ngpu2"):
         for f, data in outs[mode].items():
             assert data == single[f], f"{mode}: {f} differs from the single-GPU file"
