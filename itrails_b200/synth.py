@@ -9,25 +9,66 @@ import numpy as np
 from .read_data import _build_tables, get_obs_state_dct  # noqa: F401
 
 
-def sample_block(a, b, pi, T, rng, p_n=0.01):
-    """One block of ``T`` columns as int64 symbol indices (like maf_parser's output)."""
+class _Sampler:
+    """Inverse-CDF tables of one model, shared by the blocks drawn from it."""
+
+    def __init__(self, a, b, pi):
+        a = np.asarray(a, dtype=np.float64)
+        self.K = a.shape[0]
+        self.leave = 1.0 - np.clip(np.diag(a), 0.0, 1.0 - 1e-12)
+        off = a.copy()
+        np.fill_diagonal(off, 0.0)
+        off /= off.sum(1, keepdims=True)
+        self.jump = [row.tolist() for row in np.cumsum(off, axis=1)]
+        self.start = np.cumsum(pi / np.sum(pi)).tolist()
+        emit = np.cumsum(b / b.sum(1, keepdims=True), axis=1)
+        emit[:, -1] = 1.0
+        # one sorted table for all states: entry 256 k + j = k + CDF_k(j)
+        self.emit_flat = (np.arange(self.K)[:, None] + emit).ravel()
+
+
+_SAMPLERS = {}
+
+
+def _sampler(a, b, pi):
+    key = (id(a), id(b), id(pi))
+    hit = _SAMPLERS.get(key)
+    if hit is None or hit[0] is not a:
+        _SAMPLERS.clear()
+        hit = _SAMPLERS[key] = (a, _Sampler(a, b, pi))
+    return hit[1]
+
+
+def sample_block(a, b, pi, T, rng, p_n=0.01, dtype=np.int64):
+    """One block of ``T`` columns as symbol indices (like maf_parser's output): hidden
+    path by dwell-time sampling (jump chain + geometric dwell times), columns emitted from
+    the state's row of ``b``, then with probability ``p_n`` per column one random species
+    is overwritten by ``N``."""
+    import bisect
     from . import read_data as rd
     if rd._CODE_TO_INDEX is None:
         rd._build_tables()
-    K = a.shape[0]
-    stay = np.clip(np.diag(a), 0.0, 1.0 - 1e-12)
-    off = np.array(a, dtype=np.float64)
-    np.fill_diagonal(off, 0.0)
-    off /= off.sum(1, keepdims=True)
-    bc = np.cumsum(b / b.sum(1, keepdims=True), axis=1)
-    z = rng.choice(K, p=pi / pi.sum())
-    V = np.empty(T, dtype=np.int64)
-    t = 0
-    while t < T:
-        d = min(int(rng.geometric(1.0 - stay[z])), T - t)
-        V[t:t + d] = np.minimum(np.searchsorted(bc[z], rng.random(d)), 255)
-        t += d
-        z = rng.choice(K, p=off[z])
+    sm = _sampler(a, b, pi)
+    K = sm.K
+    zs, ds, total = [], [], 0
+    z = min(bisect.bisect_left(sm.start, rng.random()), K - 1)
+    while total < T:
+        n = max(16, int((T - total) * float(sm.leave.mean()) * 1.5) + 16)
+        u = rng.random(n).tolist()
+        seg = [0] * n
+        for k in range(n):
+            seg[k] = z
+            z = min(bisect.bisect_left(sm.jump[z], u[k]), K - 1)
+        seg = np.array(seg, dtype=np.int64)
+        d = rng.geometric(sm.leave[seg])
+        zs.append(seg)
+        ds.append(d)
+        total += int(d.sum())
+    seg, d = np.concatenate(zs), np.concatenate(ds)
+    state = np.repeat(seg, d)[:T]
+    # symbol = first j with CDF_state(j) > u, for all columns in one search of the flat table
+    V = np.searchsorted(sm.emit_flat, state + rng.random(T), side="right") - 256 * state
+    np.clip(V, 0, 255, out=V)
     hit = np.nonzero(rng.random(T) < p_n)[0]
     if len(hit):
         sp = rng.integers(0, 4, size=len(hit))
@@ -36,7 +77,7 @@ def sample_block(a, b, pi, T, rng, p_n=0.01):
         digits[np.arange(len(hit)), sp] = 4
         code = ((digits[:, 0] * 5 + digits[:, 1]) * 5 + digits[:, 2]) * 5 + digits[:, 3]
         V[hit] = rd._CODE_TO_INDEX[code]
-    return V
+    return V if dtype == np.int64 else V.astype(dtype)
 
 
 def block_lengths(n_blocks, total, rng, lo=50_000, hi=150_000):
@@ -52,6 +93,15 @@ def block_lengths(n_blocks, total, rng, lo=50_000, hi=150_000):
 def alignment(a, b, pi, lengths, seed, p_n=0.01):
     rng = np.random.default_rng(seed)
     return [sample_block(a, b, pi, int(T), rng, p_n) for T in lengths]
+
+
+def alignment_blocks(a, b, pi, lengths, ids, seed, p_n=0.01, dtype=np.int64):
+    """Blocks ``ids`` of the alignment whose block ``i`` has ``lengths[i]`` columns and its
+    own random stream ``(seed, i)``: any process can generate any subset of the blocks and
+    gets exactly the columns every other process would (sharded benchmarks generate only
+    their share)."""
+    return [sample_block(a, b, pi, int(lengths[int(i)]), np.random.default_rng([int(seed), int(i)]), p_n, dtype)
+            for i in ids]
 
 
 EXAMPLE_PARAMS = dict(mu=1e-8, N_AB=50000.0, N_ABC=50000.0, t_1=240000.0, t_2=40000.0,
