@@ -86,9 +86,10 @@ struct itr_ctx {
     long long *d_runinfo = nullptr;
     double *d_P = nullptr, *d_Pb = nullptr, *d_ebar = nullptr, *d_ck_a = nullptr, *d_ck_b = nullptr;
     size_t cap_P = 0, cap_Pb = 0, cap_sP = 0, cap_ebar = 0, cap_ck_a = 0, cap_ck_b = 0;
-    int64_t *d_tile_off = nullptr;
+    int64_t *d_tile_off = nullptr, *d_part_tile = nullptr;   // d_part_tile[b]: id of block b's partial last tile, or -1
     int32_t *d_tile_blk = nullptr;
-    size_t cap_tile_off = 0, cap_tile_blk = 0;
+    size_t cap_tile_off = 0, cap_tile_blk = 0, cap_part_tile = 0;
+    int64_t n_part_tiles = 0;
     int64_t n_tiles = 0;
     bool runs_valid = false, use_runs = false;
 
@@ -262,7 +263,7 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
                     ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
                     ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar, ctx->d_Pb, ctx->d_ck_a, ctx->d_ck_b,
-                    ctx->d_tile_off, ctx->d_tile_blk};
+                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -359,6 +360,10 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     std::vector<int64_t> tile_off(n_blocks + 1, 0);
     for (int64_t b = 0; b < n_blocks; ++b) tile_off[b + 1] = tile_off[b] + (off[b + 1] - off[b] + PTILE - 1) / PTILE;
     const int64_t n_tiles = tile_off[n_blocks];
+    std::vector<int64_t> part_tile(n_blocks, -1);
+    int64_t n_part = 0;
+    for (int64_t b = 0; b < n_blocks; ++b)
+        if ((off[b + 1] - off[b]) % PTILE) { part_tile[b] = tile_off[b + 1] - 1; ++n_part; }
     std::vector<int32_t> tile_blk(n_tiles);
     for (int64_t b = 0; b < n_blocks; ++b)
         std::fill(tile_blk.begin() + tile_off[b], tile_blk.begin() + tile_off[b + 1], (int32_t)b);
@@ -378,6 +383,8 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(ensure(ctx->d_chunk_blk, ctx->cap_chunk_blk, (size_t)std::max<int64_t>(n_chunks, 1)));
     CK(ensure(ctx->d_tile_off, ctx->cap_tile_off, (size_t)(n_blocks + 1)));
     CK(ensure(ctx->d_tile_blk, ctx->cap_tile_blk, (size_t)std::max<int64_t>(n_tiles, 1)));
+    CK(ensure(ctx->d_part_tile, ctx->cap_part_tile, (size_t)n_blocks));
+    CK(cudaMemcpyAsync(ctx->d_part_tile, part_tile.data(), (size_t)n_blocks * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tile_blk, tile_blk.data(), (size_t)n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_sym + n_cols, 0, 64 * sizeof(uint16_t), ctx->stream));
@@ -411,6 +418,7 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     ctx->use_runs = 2 * (hist[0] + hist[1] + hist[2] + hist[3]) > (unsigned long long)n_cols;
     ctx->runs_valid = false;
     ctx->n_tiles = n_tiles;
+    ctx->n_part_tiles = n_part;
     ctx->h_tile_off = tile_off;
     ctx->h_off.assign(off, off + n_blocks + 1);
     ctx->h_order = order;
@@ -643,6 +651,18 @@ static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
     } while (0)
 #endif
 
+#define ITR_SWITCH_KT(K, M)             \
+    switch (((K) + 3) / 4) {            \
+        case 1: M(4); break;            \
+        case 2: M(8); break;            \
+        case 3: M(12); break;           \
+        case 4: M(16); break;           \
+        case 5: M(20); break;           \
+        case 6: M(24); break;           \
+        case 7: M(28); break;           \
+        default: M(32); break;          \
+    }
+
 template <int MODE>
 static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha, cudaStream_t st, int slot,
                            int first = 0, int count = -1) {
@@ -797,6 +817,13 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     }
     const Geometry g = geometry(ctx, ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+    if (K <= 32 && (vmode ? !strcmp(vmode, "check") : ctx->use_runs)) {
+        // many chains, stable backpointers: check the cached pointer, exact scan only on a miss
+#define VCHK(KT) viterbi_check_kernel<KT><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
+        ITR_SWITCH_KT(K, VCHK)
+#undef VCHK
+        return;
+    }
 #define VIT_REG(KT)                                                        \
     viterbi_forward_kernel<KT, 1, true><<<g.grid, g.warps * 32, sh, st>>>( \
         cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
@@ -1045,18 +1072,6 @@ extern "C" int itr_viterbi_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_col
 // ---------------------------------------------------------------------------------
 // two-pass posterior launches (K <= 32, run-dominated alignments)
 // ---------------------------------------------------------------------------------
-#define ITR_SWITCH_KT(K, M)             \
-    switch (((K) + 3) / 4) {            \
-        case 1: M(4); break;            \
-        case 2: M(8); break;            \
-        case 3: M(12); break;           \
-        case 4: M(16); break;           \
-        case 5: M(20); break;           \
-        case 6: M(24); break;           \
-        case 7: M(28); break;           \
-        default: M(32); break;          \
-    }
-
 // Pass 1, one direction (dir 0: forward checkpoints, 1: backward) over the chains of `cs`.
 static void launch_checkpoint_sweep(itr_ctx *ctx, int dir, const ChainSet &cs, cudaStream_t st) {
     const int K = ctx->K, KP = ctx->KP;
@@ -1077,19 +1092,55 @@ static void launch_checkpoint_sweep(itr_ctx *ctx, int dir, const ChainSet &cs, c
     ctx->launches += 1;
 }
 
-// Pass 2 over the tiles [t0, t1) (tile ids follow the input block order).
-static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t t0, int64_t t1) {
+// Pass 2 over the blocks [b0, b1) (tile ids follow the input block order, so this is a
+// contiguous range of tiles and of result rows).  K <= 28: full 32-column tiles on the FP64
+// tensor cores, eight tiles per warp in lock step (posterior_tiles_mma_kernel); the
+// partial last tile of each block — and everything when K > 28 or ITR_POST_TILES=fma —
+// through the one-warp-per-tile FMA kernel.
+static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, int64_t b1) {
+    const int64_t t0 = ctx->h_tile_off[b0], t1 = ctx->h_tile_off[b1];
     if (t1 <= t0) return cudaSuccess;
     const int K = ctx->K, KP = ctx->KP;
+    const int sms = ctx->prop.multiProcessorCount;
     const int wt = 4;
     const size_t sht = (size_t)wt * (2 * KP + PTILE * (KP + 1) + PTILE) * sizeof(double);
-    const unsigned gt = (unsigned)std::min<int64_t>((t1 - t0 + wt - 1) / wt, (int64_t)ctx->prop.multiProcessorCount * 6);
+    static const char *mode = getenv("ITR_POST_TILES");          // experiments / tests: "fma" | "mma"
+    const bool use_mma = K <= 28 && !(mode && !strcmp(mode, "fma"));
     cudaError_t e = cudaSuccess;
+    if (use_mma) {
+        const size_t shm = (size_t)wt * 8 * (PTILE * K + 4) * sizeof(double);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024 - 1024) / (shm + 1024)));
+        const int64_t groups = (t1 - t0 + 7) / 8;
+        const unsigned gm = (unsigned)std::min<int64_t>((groups + wt - 1) / wt, (int64_t)sms * per_sm);
+#define PTM(KT)                                                                                                          \
+    do {                                                                                                                 \
+        if constexpr (KT <= 28) {                                                                                        \
+            e = cudaFuncSetAttribute(posterior_tiles_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
+            if (e == cudaSuccess)                                                                                        \
+                posterior_tiles_mma_kernel<KT><<<gm, wt * 32, shm, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, t0, t1, \
+                                                                         ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K,   \
+                                                                         ctx->d_post);                                   \
+        }                                                                                                                \
+    } while (0)
+        ITR_SWITCH_KT(K, PTM)
+#undef PTM
+        ctx->launches += 1;
+        if (e != cudaSuccess) return e;
+    }
+    // FMA kernel: every tile (list == nullptr), or the partial last tiles of the blocks
+    const int64_t *list = use_mma ? ctx->d_part_tile : nullptr;
+    const int64_t l0 = use_mma ? b0 : t0, l1 = use_mma ? b1 : t1;
+    if (use_mma) {
+        bool any = false;
+        for (int64_t b = b0; b < b1 && !any; ++b) any = (ctx->h_off[b + 1] - ctx->h_off[b]) % PTILE != 0;
+        if (!any) return cudaSuccess;
+    }
+    const unsigned gt = (unsigned)std::min<int64_t>((l1 - l0 + wt - 1) / wt, (int64_t)sms * 6);
 #define PT2(KT)                                                                                                      \
     do {                                                                                                             \
         e = cudaFuncSetAttribute(posterior_tiles_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht); \
         if (e == cudaSuccess)                                                                                        \
-            posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, t0, t1, \
+            posterior_tiles_kernel<KT><<<gt, wt * 32, sht, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, l0, l1, list, \
                                                                  ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K,       \
                                                                  ctx->d_post);                                       \
     } while (0)
@@ -1186,7 +1237,7 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                 for (int r = 0; r < n_ranges; ++r) {
                     const int64_t b0 = (int64_t)nb * r / n_ranges, b1 = (int64_t)nb * (r + 1) / n_ranges;
                     if (b1 <= b0) continue;
-                    CK(launch_post_tiles(ctx, st, ctx->h_tile_off[b0], ctx->h_tile_off[b1]));
+                    CK(launch_post_tiles(ctx, st, b0, b1));
                     if (ctx->stream_ranges > 0) {
                         while (ctx->range_events.size() <= ctx->range_col_end.size()) {
                             cudaEvent_t e = nullptr;
@@ -1208,9 +1259,7 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                 if (gi == 0) phase_begin(ctx, ITR_PH_POST_COMBINE, sf);
                 for (int q = last - 1; q >= first; --q) {
                     const int32_t blk = ctx->h_order[q];
-                    const int64_t t0 = ctx->h_tile_off[blk], t1 = ctx->h_tile_off[blk + 1];
-                    if (t1 <= t0) continue;
-                    CK(launch_post_tiles(ctx, sf, t0, t1));
+                    CK(launch_post_tiles(ctx, sf, blk, blk + 1));
                     if (!post) continue;
                     CK(cudaEventRecord(ctx->grp_events[2 * gi], sf));
                     if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sf); ctx->tr_k.push_back(e); }

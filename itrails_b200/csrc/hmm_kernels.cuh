@@ -737,9 +737,13 @@ template <int KT>
 __global__ void __launch_bounds__(128, ITR_TILES_MINB)
 posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
                        const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
-                       int64_t g_begin, int64_t g_end, const double *__restrict__ A, const double *__restrict__ PI,
+                       int64_t g_begin, int64_t g_end, const int64_t *__restrict__ list,
+                       const double *__restrict__ A, const double *__restrict__ PI,
                        const double *__restrict__ Et, const double *__restrict__ ck_a,
                        const double *__restrict__ ck_b, int K, double *__restrict__ post) {
+    // list == nullptr: the tiles [g_begin, g_end).  Else: the tile ids list[g_begin .. g_end),
+    // negative entries skipped (the partial last tiles of a range of blocks, which the
+    // tensor-core kernel below leaves to this one).
     constexpr int KP = 32, LD = KP + 1;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -766,7 +770,9 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
         return (a0 + a1) + (a2 + a3);
     };
 
-    for (int64_t g = g_begin + (int64_t)blockIdx.x * nwarps + warp; g < g_end; g += (int64_t)gridDim.x * nwarps) {
+    for (int64_t gi = g_begin + (int64_t)blockIdx.x * nwarps + warp; gi < g_end; gi += (int64_t)gridDim.x * nwarps) {
+        const int64_t g = list ? list[gi] : gi;
+        if (g < 0) continue;
         const int blk = tile_blk[g];
         const int64_t m = g - tile_off[blk];
         const int64_t beg = off[blk], T = off[blk + 1] - beg;
@@ -822,6 +828,201 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
         for (int e = lane; e < n * K; e += 32) {
             const int col = e / K, k = e - col * K;
             out[e] = al[col * LD + k] * rcp[col];
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Pass 2 on the FP64 tensor cores: eight tiles advance in lock step, one row of an
+// m8n8k4 DMMA each (north_star (3): "batched (B x K)(K x K) contraction when many blocks
+// advance in lockstep"; tcgen05 has no FP64 kind, so the FP64 tensor path is mma.sync).
+//
+// A warp takes 8 consecutive tiles; row r = lane / 4 of every fragment is tile g0 + r.
+// X (8 x K, the eight forward or backward vectors) times a (K x K) is NQ = KT/4 k-chunks
+// by NC = ceil(KT/8) n-chunks of DMMAs, the NQ x NC fragments of `a` resident in registers
+// (28 doubles at K = 27, what one column of `a` costs the FMA kernel).  The states are
+// placed so that NO data movement is needed between columns: the k side uses state 4q + c
+// in chunk q for quad lane c (the A-fragment layout), and the n side is permuted — position
+// n of chunk nc holds state 8 nc + 4 (n & 1) + (n >> 1) — so that the C fragment a thread
+// receives (positions 2c, 2c + 1 of chunk nc) is exactly the pair of states 4(2nc) + c and
+// 4(2nc + 1) + c, i.e. its A-fragment elements of k-chunks 2nc and 2nc + 1 of the next
+// column.  Per column and 8 tiles: NQ x NC DMMAs, NQ multiplies by the emission, no
+// shared-memory exchange, no shuffles (the FMA kernel: 1 STS + 14 broadcast LDS.128 + 28
+// DFMA per tile-column).  The forward vectors of the 8 x 32 columns are kept in shared
+// memory in the output's own layout (tile r: 32 rows of K doubles), multiplied in place
+// by beta on the way back, normalised per column inside the quad, and leave as plain
+// coalesced copies.  Shared memory: 8 (32 K + 4) doubles per warp (the + 4 staggers the
+// eight tiles over the banks): 55.5 KB at K = 27, four warps = one per scheduler per SM.
+// Only full 32-column tiles are stored; the last, partial tile of a block goes through
+// posterior_tiles_kernel (list mode).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+template <int NQ>
+__device__ __forceinline__ void quad_rescale(double (&x)[NQ]) {
+    unsigned hi = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) hi = max(hi, (unsigned)__double2hiint(x[q]));
+    hi = max(hi, __shfl_xor_sync(FULL, hi, 1));
+    hi = max(hi, __shfl_xor_sync(FULL, hi, 2));
+    const int ex = (int)(hi >> 20);
+    if (ex != 0 && ex < 0x7ff) {
+        const double sc = __hiloint2double((2046 - ex) << 20, 0);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) x[q] *= sc;
+    }
+}
+
+#ifndef ITR_MMA_UNROLL
+#define ITR_MMA_UNROLL 4
+#endif
+constexpr int MMA_UNROLL = ITR_MMA_UNROLL;
+
+template <int KT>
+__global__ void __launch_bounds__(128, 1)
+posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
+                           const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
+                           int64_t g_begin, int64_t g_end, const double *__restrict__ A,
+                           const double *__restrict__ PI, const double *__restrict__ Et,
+                           const double *__restrict__ ck_a, const double *__restrict__ ck_b, int K,
+                           double *__restrict__ post) {
+    static_assert(KT % 4 == 0 && KT <= 32, "KT is K rounded up to a multiple of 4");
+    constexpr int KP = 32, NQ = KT / 4, NC = (KT + 7) / 8;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int r = lane >> 2, c = lane & 3;
+    const int TS = PTILE * K + 4;                         // doubles per tile; (TS mod 16 == 4: see above)
+    double *al = smem + (size_t)warp * 8 * TS;
+    double *alr = al + (size_t)r * TS + c;                // + state 4q + c
+    // B fragments: element [k = c][n = r] of the (4 x 8) block (q, nc) of `a`
+    double B[NQ][NC];
+    {
+        const int n_state = 4 * (r & 1) + (r >> 1);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int nc = 0; nc < NC; ++nc) B[q][nc] = __ldg(A + (size_t)(4 * q + c) * KP + 8 * nc + n_state);
+    }
+    bool live[NQ];                                        // state 4q + c exists
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) live[q] = 4 * q + c < K;
+    const double *etc = Et + c;
+
+    // y = x @ a for the eight rows; y comes back in the layout x is consumed in
+    auto step = [&](const double (&x)[NQ], double (&y)[2 * NC]) {
+#pragma unroll
+        for (int j = 0; j < 2 * NC; ++j) y[j] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int nc = 0; nc < NC; ++nc) dmma_884(y[2 * nc], y[2 * nc + 1], x[q], B[q][nc]);
+    };
+
+    const int64_t stride = (int64_t)gridDim.x * nwarps * 8;
+    for (int64_t g0 = g_begin + ((int64_t)blockIdx.x * nwarps + warp) * 8; g0 < g_end; g0 += stride) {
+        const bool in = g0 + r < g_end;
+        const int64_t g = in ? g0 + r : g_end - 1;
+        const int blk = tile_blk[g];
+        const int64_t m = g - tile_off[blk];
+        const int64_t beg = off[blk], T = off[blk + 1] - beg;
+        const int64_t t0 = m * PTILE;
+        const bool full = in && (T - t0 >= PTILE);        // rows that are stored
+        // (symbols may be read up to 33 columns past a short tile: into the next block or the
+        // 64 zero columns behind the alignment — valid symbols either way, results discarded)
+        const uint16_t *sp = sym + beg + t0;
+
+        // ---- forward through the tile -------------------------------------------------
+        double x[NQ], e[NQ], pi0[NQ];
+        unsigned s_nxt = __ldg(sp + 1);
+        {
+            const unsigned s0 = __ldg(sp);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                x[q] = __ldg(ck_a + (size_t)g * KP + 4 * q + c);       // (tile 0 of a block: unused slot, finite)
+                e[q] = __ldg(etc + (size_t)s0 * KP + 4 * q);
+                pi0[q] = __ldg(PI + 4 * q + c);
+            }
+        }
+#pragma unroll MMA_UNROLL
+        for (int i = 0; i < PTILE; ++i) {
+            const unsigned s_n2 = __ldg(sp + i + 2);
+            double en[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
+            double y[2 * NC];
+            step(x, y);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[q] = y[q] * e[q];
+            if (i == 0 && m == 0) {                       // first column of a block: pi * e(V_0)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) x[q] = pi0[q] * e[q];
+            }
+            if ((i & 7) == 7) quad_rescale<NQ>(x);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (live[q]) alr[i * K + 4 * q] = x[q];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) e[q] = en[q];
+            s_nxt = s_n2;
+        }
+        // ---- backward through the tile: alpha * beta, normalised, in place ----------------
+        double b[NQ];
+        {
+            const bool last = (t0 + PTILE >= T);
+            const unsigned s31 = __ldg(sp + PTILE - 1);
+            s_nxt = __ldg(sp + PTILE - 2);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                b[q] = last ? (live[q] ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + 4 * q + c);
+                e[q] = __ldg(etc + (size_t)s31 * KP + 4 * q);
+            }
+        }
+#pragma unroll MMA_UNROLL
+        for (int i = PTILE - 1; i >= 0; --i) {
+            const unsigned s_n2 = __ldg(sp + (i >= 2 ? i - 2 : 0));
+            double en[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
+            double p[NQ], sum = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                p[q] = live[q] ? alr[i * K + 4 * q] * b[q] : 0.0;
+                sum += p[q];
+            }
+            // next beta: (beta_i * e_i) @ a  (reference orientation, optimizer.py:210)
+            double xin[NQ], y[2 * NC];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) xin[q] = b[q] * e[q];
+            step(xin, y);
+            sum += __shfl_xor_sync(FULL, sum, 1);
+            sum += __shfl_xor_sync(FULL, sum, 2);
+            const double inv = 1.0 / sum;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (live[q]) alr[i * K + 4 * q] = p[q] * inv;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) b[q] = y[q];
+            if ((i & 7) == 0) quad_rescale<NQ>(b);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) e[q] = en[q];
+            s_nxt = s_n2;
+        }
+        __syncwarp();
+        // ---- the eight tiles leave as plain coalesced copies ----------------------------------
+        const long long col0 = (long long)(beg + t0);
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr) {
+            if (!__shfl_sync(FULL, (int)full, 4 * rr)) continue;
+            double *out = post + (size_t)__shfl_sync(FULL, col0, 4 * rr) * K;
+            const double *src = al + (size_t)rr * TS;
+            const int n = PTILE * K;
+#pragma unroll 4
+            for (int j = lane; j < n; j += 32) out[j] = src[j];
         }
         __syncwarp();
     }
@@ -1311,6 +1512,127 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             const int j = lane + 32 * s;
             if (j < K && (bidx == 0x7fffffff || om[s] > best)) { best = om[s]; bidx = j; }
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, bidx, o);
+            if (oi != 0x7fffffff && (bidx == 0x7fffffff || ob > best || (ob == best && oi < bidx))) {
+                best = ob; bidx = oi;
+            }
+        }
+        if (lane == 0) final_state[blk] = bidx;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, double M);
+
+// ---------------------------------------------------------------------------------
+// Viterbi forward sweep for MANY chains (K <= 32): verify the cached pointer first.
+//
+// With thousands of blocks (config 4: 2 500 chains on 592 schedulers) the sweep is bound
+// by issue slots and the FP64 pipe, not by latency, and the K-way arg-max of
+// viterbi_forward_kernel costs ~200 instructions per column (a compare and three selects
+// per predecessor).  The backpointer vector changes in only ~2 % of the columns, so lane j
+// keeps its previous pointer p_j and only CHECKS it: all K sums s_i = fl(omega_i + log a_ij)
+// are formed as before, but each is merely compared with s_p (one DSETP and a predicated
+// count, no selects, no index bookkeeping).  The pointer is kept iff s_p is the strict,
+// unique maximum (count of s_i >= s_p is exactly one — itself; any tie goes to the slow
+// path) and the emission add can be hoisted (same test as viterbi_forward_kernel); then the
+// column's result is, by construction, what the full scan returns: same adds, same first
+// maximiser.  If any lane fails, the whole warp redoes the column with the exact scan
+// (tournament, hoisting test, literal two-add fallback) and refreshes its pointers.
+// Bit-identical to viterbi_forward_kernel; ~2.3x fewer instructions per column.
+// ---------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256)
+viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
+                     const double *__restrict__ OM0, int K,
+                     uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
+    constexpr int KP = 32;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xs = smem + (size_t)warp * 2 * KP;
+    const int n_chains = cs.n_blocks;
+    const int K4 = (K + 3) & ~3;
+    const double *etl = LEt + lane;
+    Cols<KT, 1, true> lacol;
+    lacol.load(LA, KP, lane);
+
+    for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
+        const int blk = cs.order[c];
+        const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
+        const SymTile st{cs.sym + beg, T};
+        uint8_t *bpt = bp + (size_t)beg * KP + lane + KP;        // row of column t = 1
+
+        int p = lane;                                            // cached pointer: "stay"
+        double la_p = __ldg(LA + (size_t)lane * KP + lane);
+        unsigned vcur = st.load(0, lane), vnxt = st.load(32, lane);
+        double om = __ldg(OM0 + (size_t)blk * KP + lane);
+        double e1 = __ldg(etl + __shfl_sync(FULL, vcur, 1) * KP), e2 = __ldg(etl + __shfl_sync(FULL, vcur, 2) * KP);
+        unsigned vpre = tile_symbol(vcur, vnxt, 3);              // symbol of the column two ahead
+        int buf = 0;
+        auto column = [&](int s32) {
+            double *xb = xs + buf * KP;
+            xb[lane] = om;
+            __syncwarp();
+            buf ^= 1;
+            const double e3 = __ldg(etl + vpre * KP);
+            vpre = tile_symbol(vcur, vnxt, s32 + 4);
+            const double s_p = __dadd_rn(xb[p], la_p);
+            const double2 *x2 = reinterpret_cast<const double2 *>(xb);
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < KT; i += 2) {
+                const double2 pq = x2[i / 2];
+                cnt += (__dadd_rn(pq.x, lacol.c[i]) >= s_p) ? 1 : 0;
+                cnt += (__dadd_rn(pq.y, lacol.c[i + 1]) >= s_p) ? 1 : 0;
+            }
+            double M = __dadd_rn(s_p, e1);
+            const bool bad = (lane < K) & ((cnt != 1) | viterbi_hoist_unsafe(s_p, e1, M));
+            if (__builtin_expect(__any_sync(FULL, bad), 0)) {
+                // exact column: tournament over all predecessors, then the hoisting test
+                double sv[KT];
+                int ix[KT];
+#pragma unroll
+                for (int i = 0; i < KT; i += 2) {
+                    const double2 pq = x2[i / 2];
+                    sv[i] = __dadd_rn(pq.x, lacol.c[i]);
+                    sv[i + 1] = __dadd_rn(pq.y, lacol.c[i + 1]);
+                    ix[i] = i;
+                    ix[i + 1] = i + 1;
+                }
+                tournament<KT>(sv, ix);
+                M = __dadd_rn(sv[0], e1);
+                int arg = ix[0];
+                if (__any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(sv[0], e1, M))) {
+                    const ScanResult r = viterbi_exact_scan(xb, LA + lane, KP, K4, e1);
+                    M = r.best;
+                    arg = r.arg;
+                }
+                if (arg != p) {
+                    p = arg;
+                    la_p = __ldg(LA + (size_t)p * KP + lane);
+                }
+            }
+            om = M;
+            *bpt = (uint8_t)p;
+            bpt += KP;
+            e1 = e2;
+            e2 = e3;
+        };
+        int64_t t0 = 0;
+        for (; t0 + 32 < T; t0 += 32) {
+#pragma unroll UNROLL_VIT
+            for (int s32 = 0; s32 < 32; ++s32) column(s32);
+            vcur = vnxt;
+            vnxt = st.load(t0 + 64, lane);
+        }
+#pragma unroll 1
+        for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32);
+        // first argmax of omega_{T-1}
+        double best = (lane < K) ? om : -CUDART_INF;
+        int bidx = (lane < K) ? lane : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             const double ob = __shfl_xor_sync(FULL, best, o);
