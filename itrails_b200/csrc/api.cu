@@ -1014,6 +1014,12 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
     // A posterior on its way to the host is PCIe bound (2 GB); its kernels go first, so
     // that the download starts early, and this recursion runs under the transfer.
     if (ctx->post_download) CK(cudaStreamWaitEvent(st, ctx->ev_post_compute, 0));
+    // With thousands of chains the sweep fills every SM for tens of milliseconds (one
+    // register-limited CTA each), and a model build enqueued just before it — a chain of
+    // small kernels — would crawl behind it with the log-likelihood and the posterior
+    // waiting for the model (measured at config 4: build 1 -> 57 ms inside a step).  There the
+    // sweep starts after the build; with few chains (config 2) it overlaps it as before.
+    if (ctx->n_blocks > (int64_t)3 * ctx->prop.multiProcessorCount / 2) CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
     CK(cudaMemcpyAsync(t_la, log_a, n_la * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t_le, log_E, n_le * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t_om, omega0, n_om * sizeof(double), cudaMemcpyHostToDevice, st));

@@ -1544,8 +1544,35 @@ __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, do
 // (tournament, hoisting test, literal two-add fallback) and refreshes its pointers.
 // Bit-identical to viterbi_forward_kernel; ~2.3x fewer instructions per column.
 // ---------------------------------------------------------------------------------
+// One exact column for the calling warp (all 32 lanes): tournament over all predecessors
+// with the column of log a read back from L1, the hoisting test, and the literal two-add
+// scan when the test fires.  Cold path of viterbi_check_kernel.
 template <int KT>
-__global__ void __launch_bounds__(256)
+__device__ __noinline__ ScanResult viterbi_full_column(const double *xb, const double *lac, int K, int K4, double le) {
+    constexpr int KP = 32;
+    const int lane = threadIdx.x & 31;
+    const double2 *x2 = reinterpret_cast<const double2 *>(xb);
+    double sv[KT];
+    int ix[KT];
+#pragma unroll
+    for (int i = 0; i < KT; i += 2) {
+        const double2 pq = x2[i / 2];
+        sv[i] = __dadd_rn(pq.x, __ldg(lac + (size_t)i * KP));
+        sv[i + 1] = __dadd_rn(pq.y, __ldg(lac + (size_t)(i + 1) * KP));
+        ix[i] = i;
+        ix[i + 1] = i + 1;
+    }
+    tournament<KT>(sv, ix);
+    ScanResult r{__dadd_rn(sv[0], le), ix[0]};
+    if (__any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(sv[0], le, r.best))) r = viterbi_exact_scan(xb, lac, KP, K4, le);
+    return r;
+}
+
+#ifndef ITR_VCHK_MINB
+#define ITR_VCHK_MINB 2
+#endif
+template <int KT>
+__global__ void __launch_bounds__(256, ITR_VCHK_MINB)
 viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                      const double *__restrict__ OM0, int K,
                      uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
@@ -1581,37 +1608,22 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
             vpre = tile_symbol(vcur, vnxt, s32 + 4);
             const double s_p = __dadd_rn(xb[p], la_p);
             const double2 *x2 = reinterpret_cast<const double2 *>(xb);
-            int cnt = 0;
+            int cnt[4] = {0, 0, 0, 0};                           // (four short chains of predicated adds)
 #pragma unroll
             for (int i = 0; i < KT; i += 2) {
                 const double2 pq = x2[i / 2];
-                cnt += (__dadd_rn(pq.x, lacol.c[i]) >= s_p) ? 1 : 0;
-                cnt += (__dadd_rn(pq.y, lacol.c[i + 1]) >= s_p) ? 1 : 0;
+                cnt[(i / 2) & 3] += (__dadd_rn(pq.x, lacol.c[i]) >= s_p) ? 1 : 0;
+                cnt[(i / 2 + 2) & 3] += (__dadd_rn(pq.y, lacol.c[i + 1]) >= s_p) ? 1 : 0;
             }
             double M = __dadd_rn(s_p, e1);
-            const bool bad = (lane < K) & ((cnt != 1) | viterbi_hoist_unsafe(s_p, e1, M));
+            const bool bad = (lane < K) & (((cnt[0] + cnt[1]) + (cnt[2] + cnt[3]) != 1) | viterbi_hoist_unsafe(s_p, e1, M));
             if (__builtin_expect(__any_sync(FULL, bad), 0)) {
-                // exact column: tournament over all predecessors, then the hoisting test
-                double sv[KT];
-                int ix[KT];
-#pragma unroll
-                for (int i = 0; i < KT; i += 2) {
-                    const double2 pq = x2[i / 2];
-                    sv[i] = __dadd_rn(pq.x, lacol.c[i]);
-                    sv[i + 1] = __dadd_rn(pq.y, lacol.c[i + 1]);
-                    ix[i] = i;
-                    ix[i + 1] = i + 1;
-                }
-                tournament<KT>(sv, ix);
-                M = __dadd_rn(sv[0], e1);
-                int arg = ix[0];
-                if (__any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(sv[0], e1, M))) {
-                    const ScanResult r = viterbi_exact_scan(xb, LA + lane, KP, K4, e1);
-                    M = r.best;
-                    arg = r.arg;
-                }
-                if (arg != p) {
-                    p = arg;
+                // exact column (out of line: its K sums and indices would not fit next to
+                // the resident column of log a)
+                const ScanResult r = viterbi_full_column<KT>(xb, LA + lane, K, K4, e1);
+                M = r.best;
+                if (r.arg != p) {
+                    p = r.arg;
                     la_p = __ldg(LA + (size_t)p * KP + lane);
                 }
             }

@@ -7,18 +7,26 @@
 // The reference goes through Biopython's AlignIO.parse(file, "maf") and resolves every
 // column with an O(625) list.index.  Here the file is mmap'ed, block boundaries are
 // found in one pass, blocks are parsed by a pool of threads, and a column is converted
-// with a 256-entry byte table and base-5 arithmetic.  Semantics kept:
-//   * a block is the run of lines after an "a" line up to a blank line / next "a" / EOF;
-//     only "s src start size strand srcSize text" rows matter; '#', track, i/e/q lines
-//     are ignored;
+// with a 256-entry byte table and base-5 arithmetic.  Semantics kept (the block iterator
+// is Biopython 1.84's MafIterator, Bio/AlignIO/MafIO.py, restated in oracle/maf_oracle.py):
+//   * outside a block a line whose first character is 'a' opens one (as many key=value
+//     words as '=' signs, else an error); every other line (##maf, '#', track, blank) is
+//     skipped;
+//   * inside a block: first character 's' = a row "s src start size strand srcSize text"
+//     with exactly 7 fields (else an error; strand '-' is -1, anything else +1; a '.' in the
+//     text copies the letter of the block's FIRST row); 'i', 'e', 'q', '#' lines are
+//     skipped; a blank line or the end of the file closes the block; any other line —
+//     another 'a' line without a blank line before it, an indented row — is an error, and
+//     so are rows of unequal length;  "\r\n" line ends are accepted;
 //   * species = src up to the first '.'; rows of species outside the list are skipped;
 //     if a species occurs twice the last row wins (dict assignment, read_data.py:108-109);
 //   * symbols: block kept iff all four species are present (read_data.py:110);
 //     '-' counts as 'N' (:109), letters are upper-cased (:114), any other character is an
 //     error (list.index raises ValueError);
 //   * coordinates: block kept iff exactly four rows belong to listed species (:171-173,
-//     :181); forward strand starts at `start`, reverse strand at srcSize - start and runs
-//     backwards (:197-201, :213); gaps and blocks without the reference species give -9.
+//     :181 — a duplicated species makes five and drops the block from the coordinate
+//     list only); forward strand starts at `start`, reverse strand at srcSize - start and
+//     runs backwards (:197-201, :213); gaps and blocks without the reference species give -9.
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -29,6 +37,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <thread>
 #include <vector>
@@ -50,6 +59,7 @@ struct BlockOut {
     bool keep_sym = false, keep_coord = false;
     std::vector<uint16_t> sym;
     std::vector<int64_t> coord;
+    std::deque<std::string> dots;     // rows whose '.' were replaced (stable addresses)
     std::string err;
 };
 
@@ -85,30 +95,32 @@ inline const char *skip_tok(const char *p, const char *e) {
     while (p < e && *p != ' ' && *p != '\t' && *p != '\r') ++p;
     return p;
 }
-bool parse_i64(const char *b, const char *e, int64_t *out) {
+bool parse_i64(const char *b, const char *e, int64_t *out) {       // Python int(): optional sign, digits
+    bool neg = false;
+    if (b < e && (*b == '+' || *b == '-')) neg = *b++ == '-';
     if (b == e) return false;
     int64_t v = 0;
     for (const char *p = b; p < e; ++p) {
         if (*p < '0' || *p > '9') return false;
         v = v * 10 + (*p - '0');
     }
-    *out = v;
+    *out = neg ? -v : v;
     return true;
 }
 
-// Parses the "s" rows of one block [b, e).
+// Parses the "s" rows of one block [b, e): every line whose FIRST character is 's'
+// (the boundary pass has already rejected lines that may not appear inside a block).
 bool parse_rows(const char *b, const char *e, std::vector<Row> &rows, std::string &err) {
     rows.clear();
     const char *p = b;
     while (p < e) {
         const char *nl = (const char *)memchr(p, '\n', e - p);
         const char *le = nl ? nl : e;
-        const char *q = skip_ws(p, le);
-        if (q < le && *q == 's' && q + 1 < le && (q[1] == ' ' || q[1] == '\t')) {
-            const char *f[7], *g[7];
+        if (p < le && *p == 's') {
+            const char *f[8], *g[8];
             int n = 0;
-            const char *t = q;
-            while (n < 7) {
+            const char *t = p;
+            while (n < 8) {
                 t = skip_ws(t, le);
                 if (t >= le || *t == '\r') break;
                 f[n] = t;
@@ -116,20 +128,19 @@ bool parse_rows(const char *b, const char *e, std::vector<Row> &rows, std::strin
                 g[n] = t;
                 ++n;
             }
-            const char *rest = skip_ws(t, le);
-            if (n != 7 || (rest < le && *rest != '\r')) {
-                err = "malformed MAF sequence line: " + std::string(q, std::min<size_t>(60, le - q));
+            if (n != 7) {
+                err = "Error parsing alignment - 's' line must have 7 fields: " + std::string(p, std::min<size_t>(60, le - p));
                 return false;
             }
             Row r{};
+            int64_t size_field = 0;
             r.src = f[1];
             r.src_len = g[1] - f[1];
-            if (!parse_i64(f[2], g[2], &r.start) || !parse_i64(f[5], g[5], &r.src_size) || g[4] - f[4] != 1 ||
-                (*f[4] != '+' && *f[4] != '-')) {
-                err = "malformed MAF sequence line: " + std::string(q, std::min<size_t>(60, le - q));
+            if (!parse_i64(f[2], g[2], &r.start) || !parse_i64(f[3], g[3], &size_field) || !parse_i64(f[5], g[5], &r.src_size)) {
+                err = "invalid integer in MAF sequence line: " + std::string(p, std::min<size_t>(60, le - p));
                 return false;
             }
-            r.strand = *f[4] == '+' ? 1 : -1;
+            r.strand = (g[4] - f[4] == 1 && *f[4] == '-') ? -1 : 1;
             r.text = f[6];
             r.text_len = g[6] - f[6];
             rows.push_back(r);
@@ -152,10 +163,27 @@ void do_block(const char *b, const char *e, const char *const sp[4], const size_
     std::vector<Row> rows;
     if (!parse_rows(b, e, rows, out.err)) return;
     if (rows.empty()) return;
+    // a '.' stands for the letter of the block's first row at that column (MafIterator);
+    // the substituted text lives in out.dots for the lifetime of the block
+    if (memchr(rows[0].text, '.', rows[0].text_len)) {
+        out.err = "Found dot/period in first sequence of alignment";
+        return;
+    }
+    for (size_t k = 1; k < rows.size(); ++k) {
+        Row &r = rows[k];
+        if (!memchr(r.text, '.', r.text_len)) continue;
+        const size_t n = std::min(r.text_len, rows[0].text_len);      // (zip() stops at the shorter one)
+        out.dots.emplace_back(r.text, n);
+        std::string &t = out.dots.back();
+        for (size_t i = 0; i < n; ++i)
+            if (t[i] == '.') t[i] = rows[0].text[i];
+        r.text = t.data();
+        r.text_len = n;
+    }
     const size_t len = rows[0].text_len;
     for (const Row &r : rows)
         if (r.text_len != len) {
-            out.err = "sequences in a MAF block must have equal length";
+            out.err = "Sequences must all be the same length";
             return;
         }
     const Row *pick[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -253,21 +281,44 @@ extern "C" int itr_maf_read(const char *path, const char *const species[4], cons
     }
     madvise((void *)base, size, MADV_SEQUENTIAL);
     const char *end = base + size;
-    // block boundaries: [start of the line after an "a" line, start of the next "a" line / blank line)
+    // block boundaries with MafIterator's state machine: [line after an "a" line, the blank
+    // line that closes the block / end of file)
     std::vector<std::pair<const char *, const char *>> blocks;
     {
         const char *p = base, *cur = nullptr;
-        while (p < end) {
+        std::string bad;
+        while (p < end && bad.empty()) {
             const char *nl = (const char *)memchr(p, '\n', end - p);
             const char *le = nl ? nl : end;
             const char *q = skip_ws(p, le);
             const bool blank = (q == le) || (*q == '\r' && q + 1 == le);
-            const bool a_line = !blank && *q == 'a' && (q + 1 == le || q[1] == ' ' || q[1] == '\t' || q[1] == '\r');
-            if (blank || a_line) {
-                if (cur) blocks.push_back({cur, p});
-                cur = a_line ? (nl ? nl + 1 : end) : nullptr;
+            const char tag = p < le ? *p : '\0';
+            if (cur) {
+                if (blank) {
+                    blocks.push_back({cur, p});
+                    cur = nullptr;
+                } else if (tag != 's' && tag != 'i' && tag != 'e' && tag != 'q' && tag != '#') {
+                    bad = "Error parsing alignment - unexpected line: " + std::string(p, std::min<size_t>(60, le - p));
+                }
+            } else if (tag == 'a') {
+                // as many whitespace-separated words after the first as '=' signs
+                size_t words = 0, eqs = 0;
+                bool in_word = false;
+                for (const char *c = p; c < le; ++c) {
+                    if (*c == '=') ++eqs;
+                    const bool ws = (*c == ' ' || *c == '\t' || *c == '\r');
+                    if (!ws && !in_word) ++words;
+                    in_word = !ws;
+                }
+                if (words - 1 != eqs) bad = "Error parsing alignment - invalid key in 'a' line";
+                cur = nl ? nl + 1 : end;
             }
             p = nl ? nl + 1 : end;
+        }
+        if (!bad.empty()) {
+            munmap((void *)base, size);
+            delete m;
+            return set_err(err, err_cap, bad, ITR_ERR_ARG);
         }
         if (cur) blocks.push_back({cur, end});
     }

@@ -2,11 +2,27 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``itrails_b200/`` may import this module.
 Restates read_data.py:94-117 (``maf_parser``) and read_data.py:146-220
-(``parse_coordinates``) of the reference without Biopython (absent from this image), from
-the MAF format itself: blocks opened by an ``a`` line, rows
-``s src start size strand srcSize text``, closed by a blank line.  Parity unpinned by the
-reference (it has no tests and Biopython cannot be installed here); pinned by hand-written
-MAF text with hand-computed expectations in tests/test_host.py.
+(``parse_coordinates``) of the reference, and — because those go through
+``Bio.AlignIO.parse(file, "maf")`` — the block iterator of Biopython 1.84
+(``Bio/AlignIO/MafIO.py``, ``MafIterator``; the version the reference pins, absent from
+this image and not installable here), restated from its published algorithm:
+
+* outside a block: a line starting with ``a`` opens one (its ``key=value`` words are
+  checked: as many words as ``=`` signs, else ``ValueError``); every other line —
+  ``##maf``, ``#`` comments, ``track`` lines, blank lines, anything — is skipped;
+* inside a block: a line starting with ``s`` is a sequence row and must have exactly 7
+  whitespace-separated fields (``ValueError`` otherwise); strand ``+`` is 1, ``-`` is -1,
+  anything else 1; a ``.`` in the text means "same letter as the FIRST row of the block";
+  lines starting with ``i``, ``e``, ``q``, ``#`` are skipped; a blank line (or the end of
+  the file) closes the block; ANY other line — including an ``a`` line, i.e. two blocks
+  without a blank line between them, or an indented row — is a ``ValueError``;
+* closing a block builds a ``MultipleSeqAlignment``: rows of unequal length are a
+  ``ValueError``; a block without rows is an empty alignment (skipped by both callers);
+* the file is read in text mode with universal newlines, so CRLF files parse alike.
+
+Parity is UNPINNED by the reference (it has no tests; Biopython cannot run here): the pins
+are the hand-computed cases of tests/test_maf_cases.py, one per quirk, each citing the
+read_data.py line it exercises.
 """
 import numpy as np
 
@@ -25,31 +41,43 @@ _BYTE_TO_DIGIT[ord("-")] = 4          # read_data.py:109: gaps become N
 
 
 def _maf_blocks(file):
-    """Yield one list of (src, start, size, strand, srcSize, text) per ``a`` block."""
+    """Yield one list of (src, start, size, strand, srcSize, text) per ``a`` block
+    (MafIterator of Biopython 1.84, see the module docstring)."""
     rows, in_block = [], False
-    with open(file, "rb") as fh:
-        for raw in fh:
-            line = raw.strip()
-            if not line:
-                if in_block:
-                    yield rows
-                rows, in_block = [], False
-                continue
-            tag = line[:1]
-            if tag == b"#":
-                continue
-            if tag == b"a":
-                if in_block:
-                    yield rows
+
+    def close(rows):
+        if rows and any(len(r[5]) != len(rows[0][5]) for r in rows):
+            raise ValueError("Sequences must all be the same length")      # MultipleSeqAlignment
+        return rows
+
+    with open(file, "r", newline=None) as fh:           # universal newlines, like AlignIO
+        for line in fh:
+            if in_block:
+                if line.startswith("s"):
+                    f = line.strip().split()
+                    if len(f) != 7:
+                        raise ValueError("Error parsing alignment - 's' line must have 7 fields")
+                    strand = -1 if f[4] == "-" else 1
+                    text = f[6]
+                    if "." in text:
+                        if not rows:
+                            raise ValueError("Found dot/period in first sequence of alignment")
+                        text = "".join(r if c == "." else c for c, r in zip(text, rows[0][5]))
+                    rows.append((f[1], int(f[2]), int(f[3]), strand, int(f[5]), text))
+                elif line[:1] in ("i", "e", "q", "#"):
+                    pass
+                elif not line.strip():
+                    yield close(rows)
+                    rows, in_block = [], False
+                else:
+                    raise ValueError(f"Error parsing alignment - unexpected line:\n{line}")
+            elif line.startswith("a"):
+                words = line.strip().split()[1:]
+                if len(words) != line.count("="):
+                    raise ValueError("Error parsing alignment - invalid key in 'a' line")
                 rows, in_block = [], True
-            elif tag == b"s" and in_block:
-                f = line.split()
-                if len(f) != 7:
-                    raise ValueError(f"malformed MAF sequence line: {line[:60]!r}")
-                strand = 1 if f[4] == b"+" else -1
-                rows.append((f[1].decode(), int(f[2]), int(f[3]), strand, int(f[5]), f[6]))
         if in_block:
-            yield rows
+            yield close(rows)
 
 
 def maf_parser(file, sp_lst):
@@ -73,9 +101,10 @@ def maf_parser(file, sp_lst):
         if len(dct) == 4:
             code = np.zeros(length, dtype=np.int64)
             for sp in sp_lst:
-                d = _BYTE_TO_DIGIT[np.frombuffer(dct[sp], dtype=np.uint8)]
+                raw = np.frombuffer(dct[sp].encode("latin-1", "replace"), dtype=np.uint8)
+                d = _BYTE_TO_DIGIT[raw]
                 if d.size and d.max() == 255:
-                    bad = chr(dct[sp][int(np.argmax(d == 255))])
+                    bad = dct[sp][int(np.argmax(d == 255))]
                     raise ValueError(f"'{bad}' is not a valid nucleotide in a MAF column")
                 code = code * 5 + d
             total.append(_CODE_TO_INDEX[code])
@@ -103,7 +132,7 @@ def parse_coordinates(file, sp_lst, ref):
             continue
         start, strand, srcsize, text = hit
         st = start if strand == 1 else srcsize - start
-        present = np.frombuffer(text, dtype=np.uint8) != ord("-")
+        present = np.frombuffer(text.encode("latin-1", "replace"), dtype=np.uint8) != ord("-")
         coords = np.full(len(text), -9, dtype=np.int64)
         coords[present] = st + strand * np.arange(int(present.sum()))
         tot.append(coords.tolist())
