@@ -1114,16 +1114,16 @@ static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, 
     const bool use_mma = K <= 28 && !(mode && !strcmp(mode, "fma"));
     cudaError_t e = cudaSuccess;
     if (use_mma) {
-        const size_t shm = (size_t)wt * 8 * (PTILE * K + 4) * sizeof(double);
+        const size_t shm = (size_t)MMA_PAIRS * 8 * (PTILE * K + 4) * sizeof(double);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024 - 1024) / (shm + 1024)));
         const int64_t groups = (t1 - t0 + 7) / 8;
-        const unsigned gm = (unsigned)std::min<int64_t>((groups + wt - 1) / wt, (int64_t)sms * per_sm);
+        const unsigned gm = (unsigned)std::min<int64_t>((groups + MMA_PAIRS - 1) / MMA_PAIRS, (int64_t)sms * per_sm);
 #define PTM(KT)                                                                                                          \
     do {                                                                                                                 \
         if constexpr (KT <= 28) {                                                                                        \
             e = cudaFuncSetAttribute(posterior_tiles_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
             if (e == cudaSuccess)                                                                                        \
-                posterior_tiles_mma_kernel<KT><<<gm, wt * 32, shm, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, t0, t1, \
+                posterior_tiles_mma_kernel<KT><<<gm, 64 * MMA_PAIRS, shm, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, t0, t1, \
                                                                          ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K,   \
                                                                          ctx->d_post);                                   \
         }                                                                                                                \

@@ -838,22 +838,28 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
 // m8n8k4 DMMA each (north_star (3): "batched (B x K)(K x K) contraction when many blocks
 // advance in lockstep"; tcgen05 has no FP64 kind, so the FP64 tensor path is mma.sync).
 //
-// A warp takes 8 consecutive tiles; row r = lane / 4 of every fragment is tile g0 + r.
-// X (8 x K, the eight forward or backward vectors) times a (K x K) is NQ = KT/4 k-chunks
-// by NC = ceil(KT/8) n-chunks of DMMAs, the NQ x NC fragments of `a` resident in registers
-// (28 doubles at K = 27, what one column of `a` costs the FMA kernel).  The states are
-// placed so that NO data movement is needed between columns: the k side uses state 4q + c
-// in chunk q for quad lane c (the A-fragment layout), and the n side is permuted — position
-// n of chunk nc holds state 8 nc + 4 (n & 1) + (n >> 1) — so that the C fragment a thread
-// receives (positions 2c, 2c + 1 of chunk nc) is exactly the pair of states 4(2nc) + c and
-// 4(2nc + 1) + c, i.e. its A-fragment elements of k-chunks 2nc and 2nc + 1 of the next
-// column.  Per column and 8 tiles: NQ x NC DMMAs, NQ multiplies by the emission, no
-// shared-memory exchange, no shuffles (the FMA kernel: 1 STS + 14 broadcast LDS.128 + 28
-// DFMA per tile-column).  The forward vectors of the 8 x 32 columns are kept in shared
-// memory in the output's own layout (tile r: 32 rows of K doubles), multiplied in place
-// by beta on the way back, normalised per column inside the quad, and leave as plain
-// coalesced copies.  Shared memory: 8 (32 K + 4) doubles per warp (the + 4 staggers the
-// eight tiles over the banks): 55.5 KB at K = 27, four warps = one per scheduler per SM.
+// A PAIR of warps takes 8 consecutive tiles; row r = lane / 4 of every fragment is tile
+// g0 + r.  X (8 x K, the eight forward or backward vectors) times a (K x K) is NQ = KT/4
+// k-chunks by NC = ceil(KT/8) n-chunks of DMMAs, the NQ x NC fragments of `a` resident in
+// registers (28 doubles at K = 27, what one column of `a` costs the FMA kernel).  The
+// states are placed so that NO data movement is needed between columns: the k side uses
+// state 4q + c in chunk q for quad lane c (the A-fragment layout), and the n side is
+// permuted — position n of chunk nc holds state 8 nc + 4 (n & 1) + (n >> 1) — so that the C
+// fragment a thread receives (positions 2c, 2c + 1 of chunk nc) is exactly the pair of
+// states 4(2nc) + c and 4(2nc + 1) + c, i.e. its A-fragment elements of k-chunks 2nc and
+// 2nc + 1 of the next column.  Per column and 8 tiles: NQ x NC DMMAs, NQ multiplies by the
+// emission, no shared-memory exchange, no shuffles (the FMA kernel: 1 STS + 14 broadcast
+// LDS.128 + 28 DFMA per tile-column).
+// The two warps of a pair walk the tile from both ends at once: warp 0 forward from the
+// forward checkpoint (columns 0..31), warp 1 backward from the backward checkpoint (31..0).
+// For their first 16 columns they park alpha_t / beta_t in shared memory, in the OUTPUT's
+// layout (tile r: 32 rows of K doubles); after one pair barrier each finds the other's
+// vector waiting in the slot of the column it produces, multiplies, normalises inside the
+// quad and leaves the posterior row in place; after a second barrier the eight tiles leave
+// as plain coalesced copies.  (A DMMA blocks its warp's issue slot for its 16 pipe cycles
+// — ptxas pads each with a NOP — so ONE warp per scheduler keeps the pipe only half busy
+// (measured: 50 %); two warps per scheduler fill each other's gaps, and the two-ended walk
+// is what makes eight warps fit: 8 (32 K + 4) doubles per PAIR, 55.5 KB at K = 27.)
 // Only full 32-column tiles are stored; the last, partial tile of a block goes through
 // posterior_tiles_kernel (list mode).
 // ---------------------------------------------------------------------------------
@@ -878,13 +884,18 @@ __device__ __forceinline__ void quad_rescale(double (&x)[NQ]) {
     }
 }
 
+__device__ __forceinline__ void pair_barrier(int pair) {
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
 #ifndef ITR_MMA_UNROLL
 #define ITR_MMA_UNROLL 4
 #endif
 constexpr int MMA_UNROLL = ITR_MMA_UNROLL;
+constexpr int MMA_PAIRS = 4;                       // pairs of warps per CTA
 
 template <int KT>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(64 * MMA_PAIRS, 1)
 posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
                            const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
                            int64_t g_begin, int64_t g_end, const double *__restrict__ A,
@@ -892,13 +903,14 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__re
                            const double *__restrict__ ck_a, const double *__restrict__ ck_b, int K,
                            double *__restrict__ post) {
     static_assert(KT % 4 == 0 && KT <= 32, "KT is K rounded up to a multiple of 4");
-    constexpr int KP = 32, NQ = KT / 4, NC = (KT + 7) / 8;
+    constexpr int KP = 32, NQ = KT / 4, NC = (KT + 7) / 8, HALF = PTILE / 2;
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp >> 1, role = warp & 1;          // role 0: forward half, 1: backward half
     const int r = lane >> 2, c = lane & 3;
-    const int TS = PTILE * K + 4;                         // doubles per tile; (TS mod 16 == 4: see above)
-    double *al = smem + (size_t)warp * 8 * TS;
-    double *alr = al + (size_t)r * TS + c;                // + state 4q + c
+    const int TS = PTILE * K + 4;                         // doubles per tile; TS mod 16 == 4 staggers the tiles over the banks
+    double *al = smem + (size_t)pair * 8 * TS;
+    double *alr = al + (size_t)r * TS + c;                // + column * K + 4q: state 4q + c of this row's tile
     // B fragments: element [k = c][n = r] of the (4 x 8) block (q, nc) of `a`
     double B[NQ][NC];
     {
@@ -922,9 +934,29 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__re
 #pragma unroll
             for (int nc = 0; nc < NC; ++nc) dmma_884(y[2 * nc], y[2 * nc + 1], x[q], B[q][nc]);
     };
+    // column `col` of the row's tile is final: v = (own vector) * (the other warp's, parked in its slot)
+    auto finish = [&](int col, const double (&v)[NQ]) {
+        double p[NQ], sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            p[q] = live[q] ? alr[col * K + 4 * q] * v[q] : 0.0;
+            sum += p[q];
+        }
+        sum += __shfl_xor_sync(FULL, sum, 1);
+        sum += __shfl_xor_sync(FULL, sum, 2);
+        const double inv = 1.0 / sum;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if (live[q]) alr[col * K + 4 * q] = p[q] * inv;
+    };
+    auto park = [&](int col, const double (&v)[NQ]) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if (live[q]) alr[col * K + 4 * q] = v[q];
+    };
 
-    const int64_t stride = (int64_t)gridDim.x * nwarps * 8;
-    for (int64_t g0 = g_begin + ((int64_t)blockIdx.x * nwarps + warp) * 8; g0 < g_end; g0 += stride) {
+    const int64_t stride = (int64_t)gridDim.x * MMA_PAIRS * 8;
+    for (int64_t g0 = g_begin + ((int64_t)blockIdx.x * MMA_PAIRS + pair) * 8; g0 < g_end; g0 += stride) {
         const bool in = g0 + r < g_end;
         const int64_t g = in ? g0 + r : g_end - 1;
         const int blk = tile_blk[g];
@@ -935,88 +967,96 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__re
         // (symbols may be read up to 33 columns past a short tile: into the next block or the
         // 64 zero columns behind the alignment — valid symbols either way, results discarded)
         const uint16_t *sp = sym + beg + t0;
+        double x[NQ], e[NQ];
 
-        // ---- forward through the tile -------------------------------------------------
-        double x[NQ], e[NQ], pi0[NQ];
-        unsigned s_nxt = __ldg(sp + 1);
-        {
-            const unsigned s0 = __ldg(sp);
+        if (role == 0) {
+            // ---- forward: alpha_0 .. alpha_31 ------------------------------------------------
+            double pi0[NQ];
+            unsigned s_nxt = __ldg(sp + 1);
+            {
+                const unsigned s0 = __ldg(sp);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                x[q] = __ldg(ck_a + (size_t)g * KP + 4 * q + c);       // (tile 0 of a block: unused slot, finite)
-                e[q] = __ldg(etc + (size_t)s0 * KP + 4 * q);
-                pi0[q] = __ldg(PI + 4 * q + c);
+                for (int q = 0; q < NQ; ++q) {
+                    x[q] = __ldg(ck_a + (size_t)g * KP + 4 * q + c);       // (tile 0 of a block: unused slot, finite)
+                    e[q] = __ldg(etc + (size_t)s0 * KP + 4 * q);
+                    pi0[q] = __ldg(PI + 4 * q + c);
+                }
             }
-        }
+            auto column = [&](int i) {
+                const unsigned s_n2 = __ldg(sp + i + 2);
+                double en[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
+                double y[2 * NC];
+                step(x, y);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) x[q] = y[q] * e[q];
+                if (i == 0 && m == 0) {                   // first column of a block: pi * e(V_0)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) x[q] = pi0[q] * e[q];
+                }
+                if ((i & 7) == 7) quad_rescale<NQ>(x);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) e[q] = en[q];
+                s_nxt = s_n2;
+            };
 #pragma unroll MMA_UNROLL
-        for (int i = 0; i < PTILE; ++i) {
-            const unsigned s_n2 = __ldg(sp + i + 2);
-            double en[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
-            double y[2 * NC];
-            step(x, y);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x[q] = y[q] * e[q];
-            if (i == 0 && m == 0) {                       // first column of a block: pi * e(V_0)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) x[q] = pi0[q] * e[q];
+            for (int i = 0; i < HALF; ++i) {
+                column(i);
+                park(i, x);
             }
-            if ((i & 7) == 7) quad_rescale<NQ>(x);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (live[q]) alr[i * K + 4 * q] = x[q];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) e[q] = en[q];
-            s_nxt = s_n2;
-        }
-        // ---- backward through the tile: alpha * beta, normalised, in place ----------------
-        double b[NQ];
-        {
-            const bool last = (t0 + PTILE >= T);
-            const unsigned s31 = __ldg(sp + PTILE - 1);
-            s_nxt = __ldg(sp + PTILE - 2);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                b[q] = last ? (live[q] ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + 4 * q + c);
-                e[q] = __ldg(etc + (size_t)s31 * KP + 4 * q);
-            }
-        }
+            pair_barrier(pair);                           // beta_16 .. beta_31 are parked
 #pragma unroll MMA_UNROLL
-        for (int i = PTILE - 1; i >= 0; --i) {
-            const unsigned s_n2 = __ldg(sp + (i >= 2 ? i - 2 : 0));
-            double en[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
-            double p[NQ], sum = 0.0;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                p[q] = live[q] ? alr[i * K + 4 * q] * b[q] : 0.0;
-                sum += p[q];
+            for (int i = HALF; i < PTILE; ++i) {
+                column(i);
+                finish(i, x);
             }
-            // next beta: (beta_i * e_i) @ a  (reference orientation, optimizer.py:210)
-            double xin[NQ], y[2 * NC];
+        } else {
+            // ---- backward: beta_31 .. beta_0, beta_{t-1} = (beta_t * e_t) @ a (optimizer.py:210) ----
+            unsigned s_nxt = __ldg(sp + PTILE - 2);
+            {
+                const bool last = (t0 + PTILE >= T);
+                const unsigned s31 = __ldg(sp + PTILE - 1);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) xin[q] = b[q] * e[q];
-            step(xin, y);
-            sum += __shfl_xor_sync(FULL, sum, 1);
-            sum += __shfl_xor_sync(FULL, sum, 2);
-            const double inv = 1.0 / sum;
+                for (int q = 0; q < NQ; ++q) {
+                    x[q] = last ? (live[q] ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + 4 * q + c);
+                    e[q] = __ldg(etc + (size_t)s31 * KP + 4 * q);
+                }
+            }
+            // x = beta_i on entry; leaves beta_{i-1}
+            auto column = [&](int i) {
+                const unsigned s_n2 = __ldg(sp + (i >= 2 ? i - 2 : 0));
+                double en[NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (live[q]) alr[i * K + 4 * q] = p[q] * inv;
+                for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
+                double xin[NQ], y[2 * NC];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) b[q] = y[q];
-            if ((i & 7) == 0) quad_rescale<NQ>(b);
+                for (int q = 0; q < NQ; ++q) xin[q] = x[q] * e[q];
+                step(xin, y);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) e[q] = en[q];
-            s_nxt = s_n2;
+                for (int q = 0; q < NQ; ++q) x[q] = y[q];
+                if ((i & 7) == 0) quad_rescale<NQ>(x);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) e[q] = en[q];
+                s_nxt = s_n2;
+            };
+#pragma unroll MMA_UNROLL
+            for (int i = PTILE - 1; i >= HALF; --i) {
+                park(i, x);
+                column(i);
+            }
+            pair_barrier(pair);                           // alpha_0 .. alpha_15 are parked
+#pragma unroll MMA_UNROLL
+            for (int i = HALF - 1; i >= 0; --i) {
+                finish(i, x);
+                if (i > 0) column(i);
+            }
         }
-        __syncwarp();
-        // ---- the eight tiles leave as plain coalesced copies ----------------------------------
+        pair_barrier(pair);                               // all 32 posterior rows of the 8 tiles are in place
+        // ---- the eight tiles leave as plain coalesced copies, four per warp --------------------
         const long long col0 = (long long)(beg + t0);
 #pragma unroll 1
-        for (int rr = 0; rr < 8; ++rr) {
+        for (int rr = 4 * role; rr < 4 * role + 4; ++rr) {
             if (!__shfl_sync(FULL, (int)full, 4 * rr)) continue;
             double *out = post + (size_t)__shfl_sync(FULL, col0, 4 * rr) * K;
             const double *src = al + (size_t)rr * TS;
@@ -1024,7 +1064,7 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__re
 #pragma unroll 4
             for (int j = lane; j < n; j += 32) out[j] = src[j];
         }
-        __syncwarp();
+        pair_barrier(pair);                               // the buffer may be overwritten
     }
 }
 
@@ -1535,10 +1575,10 @@ __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, do
 // viterbi_forward_kernel costs ~200 instructions per column (a compare and three selects
 // per predecessor).  The backpointer vector changes in only ~2 % of the columns, so lane j
 // keeps its previous pointer p_j and only CHECKS it: all K sums s_i = fl(omega_i + log a_ij)
-// are formed as before, but each is merely compared with s_p (one DSETP and a predicated
-// count, no selects, no index bookkeeping).  The pointer is kept iff s_p is the strict,
-// unique maximum (count of s_i >= s_p is exactly one — itself; any tie goes to the slow
-// path) and the emission add can be hoisted (same test as viterbi_forward_kernel); then the
+// are formed as before, but each is merely compared with s_p (one OR-accumulated DSETP, no
+// selects, no index bookkeeping; p itself is taken out of the scan by a -inf in the
+// resident column of log a).  The pointer is kept iff s_p is the strict, unique maximum (no
+// other s_i >= s_p: any tie goes to the slow path) and the emission add can be hoisted (same test as viterbi_forward_kernel); then the
 // column's result is, by construction, what the full scan returns: same adds, same first
 // maximiser.  If any lane fails, the whole warp redoes the column with the exact scan
 // (tournament, hoisting test, literal two-add fallback) and refreshes its pointers.
@@ -1583,8 +1623,14 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
     const int n_chains = cs.n_blocks;
     const int K4 = (K + 3) & ~3;
     const double *etl = LEt + lane;
-    Cols<KT, 1, true> lacol;
-    lacol.load(LA, KP, lane);
+    // Column `lane` of log a with the entry of the cached pointer replaced by -inf: the K
+    // sums of a column then cover every predecessor EXCEPT p, and "is s_p the strict, unique
+    // maximum" is one OR-accumulated compare per predecessor — no counting, no selects.
+    double lac[KT];
+    auto load_column_without = [&](int p) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) lac[i] = (i == p) ? -CUDART_INF : __ldg(LA + (size_t)i * KP + lane);
+    };
 
     for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
         const int blk = cs.order[c];
@@ -1594,6 +1640,7 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
 
         int p = lane;                                            // cached pointer: "stay"
         double la_p = __ldg(LA + (size_t)lane * KP + lane);
+        load_column_without(p);
         unsigned vcur = st.load(0, lane), vnxt = st.load(32, lane);
         double om = __ldg(OM0 + (size_t)blk * KP + lane);
         double e1 = __ldg(etl + __shfl_sync(FULL, vcur, 1) * KP), e2 = __ldg(etl + __shfl_sync(FULL, vcur, 2) * KP);
@@ -1608,15 +1655,15 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
             vpre = tile_symbol(vcur, vnxt, s32 + 4);
             const double s_p = __dadd_rn(xb[p], la_p);
             const double2 *x2 = reinterpret_cast<const double2 *>(xb);
-            int cnt[4] = {0, 0, 0, 0};                           // (four short chains of predicated adds)
+            bool beaten[4] = {false, false, false, false};       // (four short chains of OR-accumulated compares)
 #pragma unroll
             for (int i = 0; i < KT; i += 2) {
                 const double2 pq = x2[i / 2];
-                cnt[(i / 2) & 3] += (__dadd_rn(pq.x, lacol.c[i]) >= s_p) ? 1 : 0;
-                cnt[(i / 2 + 2) & 3] += (__dadd_rn(pq.y, lacol.c[i + 1]) >= s_p) ? 1 : 0;
+                beaten[(i / 2) & 3] |= __dadd_rn(pq.x, lac[i]) >= s_p;
+                beaten[(i / 2 + 2) & 3] |= __dadd_rn(pq.y, lac[i + 1]) >= s_p;
             }
             double M = __dadd_rn(s_p, e1);
-            const bool bad = (lane < K) & (((cnt[0] + cnt[1]) + (cnt[2] + cnt[3]) != 1) | viterbi_hoist_unsafe(s_p, e1, M));
+            const bool bad = (lane < K) & ((beaten[0] | beaten[1]) | (beaten[2] | beaten[3]) | viterbi_hoist_unsafe(s_p, e1, M));
             if (__builtin_expect(__any_sync(FULL, bad), 0)) {
                 // exact column (out of line: its K sums and indices would not fit next to
                 // the resident column of log a)
@@ -1625,6 +1672,7 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
                 if (r.arg != p) {
                     p = r.arg;
                     la_p = __ldg(LA + (size_t)p * KP + lane);
+                    load_column_without(p);
                 }
             }
             om = M;

@@ -8,7 +8,7 @@
 // column with an O(625) list.index.  Here the file is mmap'ed, block boundaries are
 // found in one pass, blocks are parsed by a pool of threads, and a column is converted
 // with a 256-entry byte table and base-5 arithmetic.  Semantics kept (the block iterator
-// is Biopython 1.84's MafIterator, Bio/AlignIO/MafIO.py, restated in oracle/maf_oracle.py):
+// is Biopython 1.84's MafIterator, Bio/AlignIO/MafIO.py):
 //   * outside a block a line whose first character is 'a' opens one (as many key=value
 //     words as '=' signs, else an error); every other line (##maf, '#', track, blank) is
 //     skipped;
