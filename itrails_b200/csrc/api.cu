@@ -88,7 +88,8 @@ struct itr_ctx {
     size_t cap_P = 0, cap_Pb = 0, cap_sP = 0, cap_ebar = 0, cap_ck_a = 0, cap_ck_b = 0;
     int64_t *d_tile_off = nullptr, *d_part_tile = nullptr;   // d_part_tile[b]: id of block b's partial last tile, or -1
     int32_t *d_tile_blk = nullptr;
-    size_t cap_tile_off = 0, cap_tile_blk = 0, cap_part_tile = 0;
+    unsigned long long *d_tile_info = nullptr;               // one word per tile (tile_table_kernel)
+    size_t cap_tile_off = 0, cap_tile_blk = 0, cap_part_tile = 0, cap_tile_info = 0;
     int64_t n_part_tiles = 0;
     int64_t n_tiles = 0;
     bool runs_valid = false, use_runs = false;
@@ -263,7 +264,7 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
                     ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
                     ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar, ctx->d_Pb, ctx->d_ck_a, ctx->d_ck_b,
-                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile};
+                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile, ctx->d_tile_info};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -364,9 +365,6 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     int64_t n_part = 0;
     for (int64_t b = 0; b < n_blocks; ++b)
         if ((off[b + 1] - off[b]) % PTILE) { part_tile[b] = tile_off[b + 1] - 1; ++n_part; }
-    std::vector<int32_t> tile_blk(n_tiles);
-    for (int64_t b = 0; b < n_blocks; ++b)
-        std::fill(tile_blk.begin() + tile_off[b], tile_blk.begin() + tile_off[b + 1], (int32_t)b);
     const int64_t n_chunks = chunk_off[n_blocks];
     std::vector<int32_t> chunk_blk(n_chunks);
     for (int64_t b = 0; b < n_blocks; ++b)
@@ -386,10 +384,14 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
     CK(ensure(ctx->d_part_tile, ctx->cap_part_tile, (size_t)n_blocks));
     CK(cudaMemcpyAsync(ctx->d_part_tile, part_tile.data(), (size_t)n_blocks * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_tile_blk, tile_blk.data(), (size_t)n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_sym + n_cols, 0, 64 * sizeof(uint16_t), ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_sym, sym, (size_t)n_cols * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    // per-tile tables are built on the device (7.8 M tiles at 250 Mb: nothing to upload)
+    CK(ensure(ctx->d_tile_info, ctx->cap_tile_info, (size_t)std::max<int64_t>(n_tiles, 1)));
+    tile_table_kernel<<<(unsigned)std::min<int64_t>(n_blocks, 4 * ctx->prop.multiProcessorCount), 256, 0, ctx->stream>>>(
+        ctx->d_off, ctx->d_tile_off, (int)n_blocks, ctx->d_tile_blk, ctx->d_tile_info);
+    ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)n_blocks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_chunk_off, chunk_off.data(), (size_t)(n_blocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_chunk_blk, chunk_blk.data(), (size_t)n_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -757,7 +759,9 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "stream", "spec", "4warp", "1warp"
     // (speculation pays when backpointers are stable, i.e. on alignments dominated by a few
     // symbols — the same test that enables run compression; else every window mispredicts)
-    const bool want_spec = vmode ? (!strcmp(vmode, "spec") || !strcmp(vmode, "stream")) : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms / 2);
+    // (up to ~3 chains per SM the decoupled sweep, one CTA per chain pulled longest-first from
+    // the queue, beats one warp per chain: 133 against ~360 cycles per column)
+    const bool want_spec = vmode ? (!strcmp(vmode, "spec") || !strcmp(vmode, "stream")) : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms);
     const bool want_stream = vmode ? !strcmp(vmode, "stream") : true;      // ("spec": the windowed predecessor)
     if (K <= 32 && want_spec && want_stream && ctx->max_T < 0x7fffffff) {
         // decoupled speculate-and-verify sweep: runner, feeder and 14 verifiers per chain
@@ -1018,8 +1022,8 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
     // register-limited CTA each), and a model build enqueued just before it — a chain of
     // small kernels — would crawl behind it with the log-likelihood and the posterior
     // waiting for the model (measured at config 4: build 1 -> 57 ms inside a step).  There the
-    // sweep starts after the build; with few chains (config 2) it overlaps it as before.
-    if (ctx->n_blocks > (int64_t)3 * ctx->prop.multiProcessorCount / 2) CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    // sweep starts after the build; with fewer chains than SMs (config 2) it overlaps it as before.
+    if (ctx->n_blocks >= (int64_t)ctx->prop.multiProcessorCount) CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
     CK(cudaMemcpyAsync(t_la, log_a, n_la * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t_le, log_E, n_le * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t_om, omega0, n_om * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1081,20 +1085,25 @@ extern "C" int itr_viterbi_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_col
 // Pass 1, one direction (dir 0: forward checkpoints, 1: backward) over the chains of `cs`.
 static void launch_checkpoint_sweep(itr_ctx *ctx, int dir, const ChainSet &cs, cudaStream_t st) {
     const int K = ctx->K, KP = ctx->KP;
-    const Geometry g = geometry(ctx, cs.n_blocks, 12);
+    // many chains: the 128-register build at two CTAs per SM (throughput); else the
+    // spill-free build (latency)
+    static const char *force = getenv("ITR_SWEEP_REGS");           // experiments: "128" | "192"
+    const bool dense = force ? !strcmp(force, "128") : cs.n_blocks > 8 * ctx->prop.multiProcessorCount;
+    const Geometry g = geometry(ctx, cs.n_blocks, dense ? 16 : 12);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
     reset_queue(cs.queue, st);
-#define CKS(KT)                                                                                                      \
-    do {                                                                                                             \
-        if (dir)                                                                                                     \
-            checkpoint_sweep_kernel<KT, 1><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_Pb,  \
-                                                                             ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_b); \
-        else                                                                                                         \
-            checkpoint_sweep_kernel<KT, 0><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_P,   \
-                                                                             ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, ctx->d_ck_a); \
+#define CKS2(KT, DIR, REGS)                                                                                          \
+    checkpoint_sweep_kernel<KT, DIR, REGS><<<g.grid, g.warps * 32, sh, st>>>(                                        \
+        cs, ctx->d_A, ctx->d_PI, ctx->d_Et, DIR ? ctx->d_Pb : ctx->d_P, ctx->d_ebar, ctx->d_isrun, ctx->d_tile_off, K, \
+        DIR ? ctx->d_ck_b : ctx->d_ck_a)
+#define CKS(KT)                                                      \
+    do {                                                             \
+        if (dir) { if (dense) CKS2(KT, 1, 128); else CKS2(KT, 1, 192); } \
+        else     { if (dense) CKS2(KT, 0, 128); else CKS2(KT, 0, 192); } \
     } while (0)
     ITR_SWITCH_KT(K, CKS)
 #undef CKS
+#undef CKS2
     ctx->launches += 1;
 }
 
@@ -1114,16 +1123,16 @@ static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, 
     const bool use_mma = K <= 28 && !(mode && !strcmp(mode, "fma"));
     cudaError_t e = cudaSuccess;
     if (use_mma) {
-        const size_t shm = (size_t)MMA_PAIRS * 8 * (PTILE * K + 4) * sizeof(double);
+        const size_t shm = (size_t)MMA_WARPS * 4 * (PTILE * K + 4) * sizeof(double);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024 - 1024) / (shm + 1024)));
-        const int64_t groups = (t1 - t0 + 7) / 8;
-        const unsigned gm = (unsigned)std::min<int64_t>((groups + MMA_PAIRS - 1) / MMA_PAIRS, (int64_t)sms * per_sm);
+        const int64_t groups = (t1 - t0 + 3) / 4;
+        const unsigned gm = (unsigned)std::min<int64_t>((groups + MMA_WARPS - 1) / MMA_WARPS, (int64_t)sms * per_sm);
 #define PTM(KT)                                                                                                          \
     do {                                                                                                                 \
         if constexpr (KT <= 28) {                                                                                        \
             e = cudaFuncSetAttribute(posterior_tiles_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
             if (e == cudaSuccess)                                                                                        \
-                posterior_tiles_mma_kernel<KT><<<gm, 64 * MMA_PAIRS, shm, st>>>(ctx->d_sym, ctx->d_off, ctx->d_tile_off, ctx->d_tile_blk, t0, t1, \
+                posterior_tiles_mma_kernel<KT><<<gm, 32 * MMA_WARPS, shm, st>>>(ctx->d_sym, ctx->d_tile_info, t0, t1, \
                                                                          ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K,   \
                                                                          ctx->d_post);                                   \
         }                                                                                                                \

@@ -607,8 +607,10 @@ constexpr int PTILE = 32;
 
 // DIR 0: forward checkpoints ck[tile] = alpha_{32 m - 1} (state entering tile m; tile 0 unused)
 // DIR 1: backward checkpoints ck[tile] = beta_{32 m + 31} (last tile of a block: not stored, it is 1)
-template <int KT, int DIR>
-__global__ void __maxnreg__(192)
+// MAXREG 192: no spills, one 8-warp CTA per SM — few chains, latency bound (config 2).
+// MAXREG 128: two CTAs per SM — thousands of chains, throughput bound (config 4).
+template <int KT, int DIR, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 checkpoint_sweep_kernel(ChainSet cs, const double *__restrict__ A, const double *__restrict__ PI,
                         const double *__restrict__ Et, const double *__restrict__ P, const double *__restrict__ ebar,
                         const uint8_t *__restrict__ isrun, const int64_t *__restrict__ tile_off, int K,
@@ -834,35 +836,62 @@ posterior_tiles_kernel(const uint16_t *__restrict__ sym, const int64_t *__restri
 }
 
 // ---------------------------------------------------------------------------------
-// Pass 2 on the FP64 tensor cores: eight tiles advance in lock step, one row of an
-// m8n8k4 DMMA each (north_star (3): "batched (B x K)(K x K) contraction when many blocks
-// advance in lockstep"; tcgen05 has no FP64 kind, so the FP64 tensor path is mma.sync).
+// Pass 2 on the FP64 tensor cores (north_star (3): "batched (B x K)(K x K) contraction when
+// many blocks advance in lockstep"; tcgen05 has no FP64 kind, so the FP64 tensor path is
+// mma.sync.m8n8k4.f64).
 //
-// A PAIR of warps takes 8 consecutive tiles; row r = lane / 4 of every fragment is tile
-// g0 + r.  X (8 x K, the eight forward or backward vectors) times a (K x K) is NQ = KT/4
-// k-chunks by NC = ceil(KT/8) n-chunks of DMMAs, the NQ x NC fragments of `a` resident in
-// registers (28 doubles at K = 27, what one column of `a` costs the FMA kernel).  The
-// states are placed so that NO data movement is needed between columns: the k side uses
-// state 4q + c in chunk q for quad lane c (the A-fragment layout), and the n side is
-// permuted — position n of chunk nc holds state 8 nc + 4 (n & 1) + (n >> 1) — so that the C
-// fragment a thread receives (positions 2c, 2c + 1 of chunk nc) is exactly the pair of
-// states 4(2nc) + c and 4(2nc + 1) + c, i.e. its A-fragment elements of k-chunks 2nc and
-// 2nc + 1 of the next column.  Per column and 8 tiles: NQ x NC DMMAs, NQ multiplies by the
-// emission, no shared-memory exchange, no shuffles (the FMA kernel: 1 STS + 14 broadcast
-// LDS.128 + 28 DFMA per tile-column).
-// The two warps of a pair walk the tile from both ends at once: warp 0 forward from the
-// forward checkpoint (columns 0..31), warp 1 backward from the backward checkpoint (31..0).
-// For their first 16 columns they park alpha_t / beta_t in shared memory, in the OUTPUT's
-// layout (tile r: 32 rows of K doubles); after one pair barrier each finds the other's
-// vector waiting in the slot of the column it produces, multiplies, normalises inside the
-// quad and leaves the posterior row in place; after a second barrier the eight tiles leave
-// as plain coalesced copies.  (A DMMA blocks its warp's issue slot for its 16 pipe cycles
-// — ptxas pads each with a NOP — so ONE warp per scheduler keeps the pipe only half busy
-// (measured: 50 %); two warps per scheduler fill each other's gaps, and the two-ended walk
-// is what makes eight warps fit: 8 (32 K + 4) doubles per PAIR, 55.5 KB at K = 27.)
+// A warp takes FOUR consecutive tiles and walks each from BOTH ends at once: rows 0-3 of
+// every 8-row fragment are the forward vectors of the four tiles, rows 4-7 their backward
+// vectors — both directions are "row vector times a" in the reference's orientation
+// (optimizer.py:187, :210), so one set of DMMAs advances all eight chains.  X (8 x K) times
+// a (K x K) is NQ = KT/4 k-chunks by NC = ceil(KT/8) n-chunks of DMMAs with the NQ x NC
+// fragments of `a` resident in registers (28 doubles at K = 27, what one column of `a` costs
+// the FMA kernel).  States are placed so that NO data movement is needed between columns:
+// the k side uses state 4q + c in chunk q for quad lane c (the A-fragment layout), and the
+// n side is permuted — position n of chunk nc holds state 8 nc + 4 (n & 1) + (n >> 1) — so
+// that the C fragment a thread receives (positions 2c, 2c + 1 of chunk nc) is exactly the
+// pair of states 4(2nc) + c and 4(2nc + 1) + c: its A-fragment elements of k-chunks 2nc and
+// 2nc + 1 for the next column.  Per step and warp: NQ x NC DMMAs and NQ multiplies by the
+// emission; no shared-memory exchange, no shuffles on the chain (the FMA kernel: 1 STS + 14
+// broadcast LDS.128 + 28 DFMA per tile-column).
+// With f_t = alpha_{t-1} @ a (the forward DMMA's output, before the emission) and
+// g_t = beta_t * e_t (the backward DMMA's input), the posterior of column t is f_t * g_t up
+// to a factor — so both directions run the SAME recurrence x <- (x @ a) * e(next column in
+// my direction), the forward rows handing over the DMMA's output and the backward rows its
+// input.  For the first 16 steps every row parks its vector in shared memory, in the
+// OUTPUT's layout (tile: 32 rows of K doubles); from step 16 on each row finds the other
+// direction's vector waiting in the slot of the column it produces, multiplies, normalises
+// inside the quad and leaves the posterior row in place; then the four tiles leave as
+// plain coalesced copies.  Shared memory: 4 (32 K + 4) doubles per warp = 27.8 KB at
+// K = 27, so EIGHT independent warps fit an SM — two per scheduler, which is what keeps the
+// pipe busy: a DMMA blocks its warp's issue slot for its 16 pipe cycles (ptxas pads each
+// with a NOP); measured, one warp per scheduler left the pipe 50 % idle.
 // Only full 32-column tiles are stored; the last, partial tile of a block goes through
 // posterior_tiles_kernel (list mode).
 // ---------------------------------------------------------------------------------
+// One 64-bit word per 32-column tile, built on the device when blocks are loaded, so that
+// pass 2 needs ONE load per tile instead of the chain tile -> block -> offsets:
+// bits 0..55 first column of the tile in the concatenated alignment, bit 60 tile starts a
+// block, bit 61 tile ends a block, bit 62 tile has all 32 columns.  Also fills tile_blk.
+constexpr unsigned long long TILE_FIRST = 1ull << 60, TILE_LAST = 1ull << 61, TILE_FULL = 1ull << 62,
+                             TILE_COL_MASK = (1ull << 56) - 1;
+__global__ void __launch_bounds__(256)
+tile_table_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ tile_off, int n_blocks,
+                  int32_t *__restrict__ tile_blk, unsigned long long *__restrict__ tile_info) {
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const int64_t beg = off[b], T = off[b + 1] - beg, g0 = tile_off[b], nt = tile_off[b + 1] - g0;
+        for (int64_t m = threadIdx.x; m < nt; m += blockDim.x) {
+            const int64_t t0 = m * PTILE;
+            unsigned long long w = (unsigned long long)(beg + t0);
+            if (m == 0) w |= TILE_FIRST;
+            if (t0 + PTILE >= T) w |= TILE_LAST;
+            if (T - t0 >= PTILE) w |= TILE_FULL;
+            tile_info[g0 + m] = w;
+            tile_blk[g0 + m] = b;
+        }
+    }
+}
+
 __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d0), "+d"(d1)
@@ -884,20 +913,15 @@ __device__ __forceinline__ void quad_rescale(double (&x)[NQ]) {
     }
 }
 
-__device__ __forceinline__ void pair_barrier(int pair) {
-    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
-}
-
 #ifndef ITR_MMA_UNROLL
 #define ITR_MMA_UNROLL 4
 #endif
 constexpr int MMA_UNROLL = ITR_MMA_UNROLL;
-constexpr int MMA_PAIRS = 4;                       // pairs of warps per CTA
+constexpr int MMA_WARPS = 8;                       // warps per CTA, four tiles each
 
 template <int KT>
-__global__ void __launch_bounds__(64 * MMA_PAIRS, 1)
-posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__restrict__ off,
-                           const int64_t *__restrict__ tile_off, const int32_t *__restrict__ tile_blk,
+__global__ void __launch_bounds__(32 * MMA_WARPS, 1)
+posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const unsigned long long *__restrict__ tile_info,
                            int64_t g_begin, int64_t g_end, const double *__restrict__ A,
                            const double *__restrict__ PI, const double *__restrict__ Et,
                            const double *__restrict__ ck_a, const double *__restrict__ ck_b, int K,
@@ -906,11 +930,12 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__re
     constexpr int KP = 32, NQ = KT / 4, NC = (KT + 7) / 8, HALF = PTILE / 2;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair = warp >> 1, role = warp & 1;          // role 0: forward half, 1: backward half
     const int r = lane >> 2, c = lane & 3;
+    const int tl = r & 3;                                 // tile of this row
+    const bool bwd = r >= 4;                              // direction of this row
     const int TS = PTILE * K + 4;                         // doubles per tile; TS mod 16 == 4 staggers the tiles over the banks
-    double *al = smem + (size_t)pair * 8 * TS;
-    double *alr = al + (size_t)r * TS + c;                // + column * K + 4q: state 4q + c of this row's tile
+    double *al = smem + (size_t)warp * 4 * TS;
+    double *alr = al + (size_t)tl * TS + c;               // + column * K + 4q: state 4q + c of this row's tile
     // B fragments: element [k = c][n = r] of the (4 x 8) block (q, nc) of `a`
     double B[NQ][NC];
     {
@@ -921,150 +946,134 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const int64_t *__re
             for (int nc = 0; nc < NC; ++nc) B[q][nc] = __ldg(A + (size_t)(4 * q + c) * KP + 8 * nc + n_state);
     }
     bool live[NQ];                                        // state 4q + c exists
+    double pi0[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) live[q] = 4 * q + c < K;
+    for (int q = 0; q < NQ; ++q) {
+        live[q] = 4 * q + c < K;
+        pi0[q] = __ldg(PI + 4 * q + c);
+    }
     const double *etc = Et + c;
 
-    // y = x @ a for the eight rows; y comes back in the layout x is consumed in
-    auto step = [&](const double (&x)[NQ], double (&y)[2 * NC]) {
-#pragma unroll
-        for (int j = 0; j < 2 * NC; ++j) y[j] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-#pragma unroll
-            for (int nc = 0; nc < NC; ++nc) dmma_884(y[2 * nc], y[2 * nc + 1], x[q], B[q][nc]);
-    };
-    // column `col` of the row's tile is final: v = (own vector) * (the other warp's, parked in its slot)
-    auto finish = [&](int col, const double (&v)[NQ]) {
-        double p[NQ], sum = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            p[q] = live[q] ? alr[col * K + 4 * q] * v[q] : 0.0;
-            sum += p[q];
+    const int64_t stride = (int64_t)gridDim.x * MMA_WARPS * 4;
+    int64_t g0 = g_begin + ((int64_t)blockIdx.x * MMA_WARPS + warp) * 4;
+    // the tile word of the NEXT group is fetched a whole group ahead, and with it the first
+    // symbols of that tile: the chain word -> symbol -> emission row is off the critical path
+    auto tile_word = [&](int64_t gg0) { return gg0 + tl < g_end ? __ldg(tile_info + gg0 + tl) : (__ldg(tile_info + g_end - 1) & ~TILE_FULL); };
+    unsigned long long w_next = g0 < g_end ? tile_word(g0) : 0ull;
+    for (; g0 < g_end; g0 += stride) {
+        const unsigned long long w = w_next;
+        const int64_t g = min(g0 + tl, g_end - 1);
+        if (g0 + stride < g_end) {
+            w_next = tile_word(g0 + stride);
+            // next group's checkpoint vectors (256 B each, two lines): into L2 now
+            if (c < 2) {
+                const double *nk = (bwd ? ck_b : ck_a) + (size_t)min(g + stride, g_end - 1) * KP + 16 * c;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nk));
+            }
         }
-        sum += __shfl_xor_sync(FULL, sum, 1);
-        sum += __shfl_xor_sync(FULL, sum, 2);
-        const double inv = 1.0 / sum;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-            if (live[q]) alr[col * K + 4 * q] = p[q] * inv;
-    };
-    auto park = [&](int col, const double (&v)[NQ]) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-            if (live[q]) alr[col * K + 4 * q] = v[q];
-    };
-
-    const int64_t stride = (int64_t)gridDim.x * MMA_PAIRS * 8;
-    for (int64_t g0 = g_begin + ((int64_t)blockIdx.x * MMA_PAIRS + pair) * 8; g0 < g_end; g0 += stride) {
-        const bool in = g0 + r < g_end;
-        const int64_t g = in ? g0 + r : g_end - 1;
-        const int blk = tile_blk[g];
-        const int64_t m = g - tile_off[blk];
-        const int64_t beg = off[blk], T = off[blk + 1] - beg;
-        const int64_t t0 = m * PTILE;
-        const bool full = in && (T - t0 >= PTILE);        // rows that are stored
+        const bool full = (w & TILE_FULL) != 0;           // tiles that are stored
+        const long long col0 = (long long)(w & TILE_COL_MASK);
+        const bool last = (w & TILE_LAST) != 0;
         // (symbols may be read up to 33 columns past a short tile: into the next block or the
         // 64 zero columns behind the alignment — valid symbols either way, results discarded)
-        const uint16_t *sp = sym + beg + t0;
+        const uint16_t *sp = sym + col0;
+        const bool first = !bwd && (w & TILE_FIRST) != 0;  // forward row at the start of a block: f_0 := pi
+        // Step s: forward rows produce column s, backward rows column 31 - s; after the DMMA the
+        // vector is multiplied by the emission of the NEXT column in the row's direction:
+        // column s itself going forward (f_s -> alpha_s), column 30 - s going backward
+        // (beta_{30-s} -> g_{30-s}).
+        auto ecol = [&](int s) { return bwd ? max(PTILE - 2 - s, 0) : s; };
         double x[NQ], e[NQ];
-
-        if (role == 0) {
-            // ---- forward: alpha_0 .. alpha_31 ------------------------------------------------
-            double pi0[NQ];
-            unsigned s_nxt = __ldg(sp + 1);
-            {
-                const unsigned s0 = __ldg(sp);
+        unsigned s_nxt = __ldg(sp + ecol(1));
+        {
+            const unsigned s0 = __ldg(sp + ecol(0)), s31 = __ldg(sp + PTILE - 1);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    x[q] = __ldg(ck_a + (size_t)g * KP + 4 * q + c);       // (tile 0 of a block: unused slot, finite)
-                    e[q] = __ldg(etc + (size_t)s0 * KP + 4 * q);
-                    pi0[q] = __ldg(PI + 4 * q + c);
+            for (int q = 0; q < NQ; ++q) {
+                e[q] = __ldg(etc + (size_t)s0 * KP + 4 * q);
+                if (bwd) {   // g_31 = beta_31 * e_31
+                    const double b31 = last ? (live[q] ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + 4 * q + c);
+                    x[q] = b31 * __ldg(etc + (size_t)s31 * KP + 4 * q);
+                } else {
+                    x[q] = __ldg(ck_a + (size_t)g * KP + 4 * q + c);      // alpha_{-1} (tile 0 of a block: unused slot, finite)
                 }
-            }
-            auto column = [&](int i) {
-                const unsigned s_n2 = __ldg(sp + i + 2);
-                double en[NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
-                double y[2 * NC];
-                step(x, y);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) x[q] = y[q] * e[q];
-                if (i == 0 && m == 0) {                   // first column of a block: pi * e(V_0)
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) x[q] = pi0[q] * e[q];
-                }
-                if ((i & 7) == 7) quad_rescale<NQ>(x);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) e[q] = en[q];
-                s_nxt = s_n2;
-            };
-#pragma unroll MMA_UNROLL
-            for (int i = 0; i < HALF; ++i) {
-                column(i);
-                park(i, x);
-            }
-            pair_barrier(pair);                           // beta_16 .. beta_31 are parked
-#pragma unroll MMA_UNROLL
-            for (int i = HALF; i < PTILE; ++i) {
-                column(i);
-                finish(i, x);
-            }
-        } else {
-            // ---- backward: beta_31 .. beta_0, beta_{t-1} = (beta_t * e_t) @ a (optimizer.py:210) ----
-            unsigned s_nxt = __ldg(sp + PTILE - 2);
-            {
-                const bool last = (t0 + PTILE >= T);
-                const unsigned s31 = __ldg(sp + PTILE - 1);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    x[q] = last ? (live[q] ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + 4 * q + c);
-                    e[q] = __ldg(etc + (size_t)s31 * KP + 4 * q);
-                }
-            }
-            // x = beta_i on entry; leaves beta_{i-1}
-            auto column = [&](int i) {
-                const unsigned s_n2 = __ldg(sp + (i >= 2 ? i - 2 : 0));
-                double en[NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
-                double xin[NQ], y[2 * NC];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) xin[q] = x[q] * e[q];
-                step(xin, y);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) x[q] = y[q];
-                if ((i & 7) == 0) quad_rescale<NQ>(x);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) e[q] = en[q];
-                s_nxt = s_n2;
-            };
-#pragma unroll MMA_UNROLL
-            for (int i = PTILE - 1; i >= HALF; --i) {
-                park(i, x);
-                column(i);
-            }
-            pair_barrier(pair);                           // alpha_0 .. alpha_15 are parked
-#pragma unroll MMA_UNROLL
-            for (int i = HALF - 1; i >= 0; --i) {
-                finish(i, x);
-                if (i > 0) column(i);
             }
         }
-        pair_barrier(pair);                               // all 32 posterior rows of the 8 tiles are in place
-        // ---- the eight tiles leave as plain coalesced copies, four per warp --------------------
-        const long long col0 = (long long)(beg + t0);
+        // one step; v = the vector this row hands over for its column
+        auto advance = [&](int s, double (&v)[NQ]) {
+            const unsigned s_n2 = __ldg(sp + ecol(s + 2));
+            double en[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
+            double y[2 * NC];
+#pragma unroll
+            for (int j = 0; j < 2 * NC; ++j) y[j] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int nc = 0; nc < NC; ++nc) dmma_884(y[2 * nc], y[2 * nc + 1], x[q], B[q][nc]);
+            if (s == 0 && first) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) y[q] = pi0[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                v[q] = bwd ? x[q] : y[q];
+                x[q] = y[q] * e[q];
+            }
+            if ((s & 7) == 7) quad_rescale<NQ>(x);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) e[q] = en[q];
+            s_nxt = s_n2;
+        };
+        {
+            double *slot = alr + (bwd ? (PTILE - 1) * K : 0);
+            const int dslot = bwd ? -K : K;
+#pragma unroll MMA_UNROLL
+            for (int s = 0; s < HALF; ++s) {              // park f_s / g_{31-s}
+                double v[NQ];
+                advance(s, v);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (live[q]) slot[4 * q] = v[q];
+                slot += dslot;
+            }
+            __syncwarp();                                 // the other direction's first 16 vectors are parked
+            if (c == 0) {                                 // next group's symbols (its tile word has arrived by now)
+                const uint16_t *ns = sym + (w_next & TILE_COL_MASK);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ns));
+            }
+#pragma unroll MMA_UNROLL
+            for (int s = HALF; s < PTILE; ++s) {          // meet the parked vector: posterior row, normalised
+                double v[NQ];
+                advance(s, v);
+                double p[NQ], ps[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    p[q] = live[q] ? slot[4 * q] * v[q] : 0.0;
+                    ps[q & 3] += p[q];
+                }
+                double sum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+                sum += __shfl_xor_sync(FULL, sum, 1);
+                sum += __shfl_xor_sync(FULL, sum, 2);
+                const double inv = 1.0 / sum;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (live[q]) slot[4 * q] = p[q] * inv;
+                slot += dslot;
+            }
+        }
+        __syncwarp();
+        // ---- the four tiles leave as plain coalesced copies ----------------------------------------
 #pragma unroll 1
-        for (int rr = 4 * role; rr < 4 * role + 4; ++rr) {
+        for (int rr = 0; rr < 4; ++rr) {
             if (!__shfl_sync(FULL, (int)full, 4 * rr)) continue;
             double *out = post + (size_t)__shfl_sync(FULL, col0, 4 * rr) * K;
             const double *src = al + (size_t)rr * TS;
             const int n = PTILE * K;
-#pragma unroll 4
+#pragma unroll 9
             for (int j = lane; j < n; j += 32) out[j] = src[j];
         }
-        pair_barrier(pair);                               // the buffer may be overwritten
+        __syncwarp();
     }
 }
 
@@ -1575,9 +1584,9 @@ __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, do
 // viterbi_forward_kernel costs ~200 instructions per column (a compare and three selects
 // per predecessor).  The backpointer vector changes in only ~2 % of the columns, so lane j
 // keeps its previous pointer p_j and only CHECKS it: all K sums s_i = fl(omega_i + log a_ij)
-// are formed as before, but each is merely compared with s_p (one OR-accumulated DSETP, no
-// selects, no index bookkeeping; p itself is taken out of the scan by a -inf in the
-// resident column of log a).  The pointer is kept iff s_p is the strict, unique maximum (no
+// are formed as before, but each is merely tested against s_p (one subtraction whose sign
+// bit is OR-accumulated: no selects, no index bookkeeping; p itself is taken out of the
+// scan by a -inf in the resident column of log a).  The pointer is kept iff s_p is the strict, unique maximum (no
 // other s_i >= s_p: any tie goes to the slow path) and the emission add can be hoisted (same test as viterbi_forward_kernel); then the
 // column's result is, by construction, what the full scan returns: same adds, same first
 // maximiser.  If any lane fails, the whole warp redoes the column with the exact scan
@@ -1655,15 +1664,24 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
             vpre = tile_symbol(vcur, vnxt, s32 + 4);
             const double s_p = __dadd_rn(xb[p], la_p);
             const double2 *x2 = reinterpret_cast<const double2 *>(xb);
-            bool beaten[4] = {false, false, false, false};       // (four short chains of OR-accumulated compares)
+            // "some s_i >= s_p" without compares: with t = pred(s_p) (the next double below
+            // s_p), s_i >= s_p <=> s_i > t <=> t - s_i < 0, and the sign of a rounded
+            // difference of two doubles is the sign of the exact one (a difference rounds to zero
+            // only when it is zero) — so the sign bits of the K differences are OR-ed together,
+            // one LOP3 per two predecessors.  (s_p = 0, -inf or NaN goes to the exact path
+            // through viterbi_hoist_unsafe below.)
+            const long long pb = __double_as_longlong(s_p);
+            const double t = __longlong_as_double(pb - ((pb >> 63) | 1));
+            unsigned sg[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int i = 0; i < KT; i += 2) {
                 const double2 pq = x2[i / 2];
-                beaten[(i / 2) & 3] |= __dadd_rn(pq.x, lac[i]) >= s_p;
-                beaten[(i / 2 + 2) & 3] |= __dadd_rn(pq.y, lac[i + 1]) >= s_p;
+                sg[(i / 2) & 3] |= (unsigned)__double2hiint(__dsub_rn(t, __dadd_rn(pq.x, lac[i]))) |
+                                   (unsigned)__double2hiint(__dsub_rn(t, __dadd_rn(pq.y, lac[i + 1])));
             }
             double M = __dadd_rn(s_p, e1);
-            const bool bad = (lane < K) & ((beaten[0] | beaten[1]) | (beaten[2] | beaten[3]) | viterbi_hoist_unsafe(s_p, e1, M));
+            const bool beaten = (int)((sg[0] | sg[1]) | (sg[2] | sg[3])) < 0;
+            const bool bad = (lane < K) & (beaten | viterbi_hoist_unsafe(s_p, e1, M));
             if (__builtin_expect(__any_sync(FULL, bad), 0)) {
                 // exact column (out of line: its K sums and indices would not fit next to
                 // the resident column of log a)

@@ -719,9 +719,12 @@ int ModelBuilder::build(cudaStream_t stream, int n_sets, const double *params, i
         sc[SC_CABC] = N_ref / N_ABC;
         sc[SC_MU] = N_ref * (4.0 / 3.0);
         double *cab = sc + SC_CUT, *cabc = cab + n_ab + 1;
-        for (int q = 0; q <= n_ab; ++q)      // cutpoints.py:5-26 (truncexpon.ppf)
-            cab[q] = cut_AB ? cut_AB[q]
-                            : -std::log1p(((double)q / n_ab) * std::expm1(-sc[SC_TAB] * sc[SC_CAB])) / sc[SC_CAB];
+        {   // cutpoints.py:5-26: truncexpon.ppf(q, b = t_AB / scale, scale = 1 / coal_AB) = -log1p(q expm1(-b)) scale,
+            // except q == 1, where scipy's ppf returns the upper end of the support, b * scale
+            const double scale = 1.0 / sc[SC_CAB], bb = sc[SC_TAB] / scale;
+            for (int q = 0; q <= n_ab; ++q)
+                cab[q] = cut_AB ? cut_AB[q] : (q == n_ab ? bb * scale : -std::log1p(((double)q / n_ab) * std::expm1(-bb)) * scale);
+        }
         for (int q = 0; q <= n_abc; ++q)     // cutpoints.py:29-45 (expon.ppf), last = +inf
             cabc[q] = cut_ABC ? cut_ABC[q]
                               : (q == n_abc ? std::numeric_limits<double>::infinity()

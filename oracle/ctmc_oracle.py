@@ -54,8 +54,12 @@ def cutpoints_AB(n_int_AB, t_AB, coal_AB):
     """Quantiles of an exponential(rate coal_AB) truncated to [0, t_AB]
     (cutpoints.py:5-26; scipy's truncexpon.ppf = -log1p(q*expm1(-b)))."""
     q = np.arange(n_int_AB + 1) / n_int_AB
-    b = t_AB * coal_AB
-    return -np.log1p(q * np.expm1(-b)) / coal_AB
+    scale = 1 / coal_AB
+    b = t_AB / scale
+    with np.errstate(divide="ignore"):
+        cut = -np.log1p(q * np.expm1(-b)) * scale
+    cut[-1] = b * scale          # rv_continuous.ppf: q == 1 returns the upper end of the support
+    return cut
 
 
 def cutpoints_ABC(n_int_ABC, coal_ABC):

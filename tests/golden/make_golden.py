@@ -43,6 +43,11 @@ PARAM_SETS = {
                   t_C=200000.0, t_2=20000.0, t_upper=300000.0, r=5e-9),
     "highrec": dict(mu=1e-8, N_AB=50000.0, N_ABC=100000.0, t_1=100000.0, t_2=150000.0,
                     t_upper=1500000.0, r=8e-8),
+    # t_2 / N_AB = 80: the AB interval is 80 coalescent units long, so the last AB cutpoint
+    # (truncexpon.ppf at q = 1) is the upper end of the support — the closed form
+    # -log1p(q expm1(-b)) / c overflows there (cutpoints.py:22-25)
+    "longab": dict(mu=1e-8, N_AB=5000.0, N_ABC=60000.0, t_1=200000.0, t_2=400000.0,
+                   t_upper=700000.0, r=1.5e-8),
 }
 
 

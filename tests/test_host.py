@@ -190,7 +190,7 @@ def test_native_maf_reader_equals_restatement(tmp_path):
 def test_cutpoints_match_scipy():
     from scipy.stats import expon, truncexpon
     import itrails_b200 as itb
-    for n, t, c in ((3, 0.8, 1.0), (5, 2.5, 0.4)):
+    for n, t, c in ((3, 0.8, 1.0), (5, 2.5, 0.4), (3, 30.0, 1.0), (4, 20.0, 4.0), (3, 800.0, 0.7)):
         q = np.arange(n + 1) / n
         np.testing.assert_allclose(itb.cutpoints_AB(n, t, c), truncexpon.ppf(q, b=t * c, scale=1 / c), rtol=1e-14, atol=1e-16)
         np.testing.assert_allclose(itb.cutpoints_ABC(n, c), expon.ppf(q, scale=1 / c), rtol=1e-14)
