@@ -245,9 +245,10 @@ class Runner:
         eng.set_model(self.a, self.b, self.pi)
         eng.set_async(True)
         if self.stream:
+            eng.posterior(fetch=False)                         # enqueued first: its rows are what the PCIe link waits for
             eng.viterbi(self.log_a, self.log_E, self.omega0, out=path_pin)
             ll = eng.loglik()
-            eng.posterior_stream(dst, slot_cols, n_slots)      # returns when the last piece is in host memory
+            eng.posterior_stream(dst, slot_cols, n_slots)      # drains it; returns when the last piece is in host memory
         else:
             eng.posterior(out=dst)          # largest download first: it overlaps the rest
             eng.viterbi(self.log_a, self.log_E, self.omega0, out=path_pin)

@@ -170,7 +170,9 @@ int itr_posterior_fetch_range(itr_ctx *ctx, int64_t col0, int64_t n_cols, double
  * [col0, col0 + n_cols) of the concatenated alignment; the slot is reused after it
  * returns; a non-zero return stops the stream (ITR_ERR_IO).  With sink == NULL the pieces
  * are only delivered into the ring.  The full result also stays on the device
- * (itr_posterior_fetch_range). */
+ * (itr_posterior_fetch_range).  In deferred mode (itr_set_async) a preceding
+ * itr_posterior(ctx, NULL) is the computation that gets drained: enqueue the posterior
+ * first, the other recursions behind it, then call this to download behind the kernels. */
 typedef int (*itr_rows_sink)(void *user, int64_t col0, int64_t n_cols, const double *rows);
 int itr_posterior_stream(itr_ctx *ctx, double *ring, int64_t slot_cols, int n_slots,
                          itr_rows_sink sink, void *user);

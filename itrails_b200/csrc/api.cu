@@ -69,6 +69,7 @@ struct itr_ctx {
     // itr_posterior_stream: pass 2 runs in `stream_ranges` contiguous block ranges; range r is
     // complete at range_events[r] and ends at column range_col_end[r]
     int stream_ranges = 0;
+    bool ranges_valid = false;                 // range_events / range_col_end describe the posterior on the device
     std::vector<cudaEvent_t> range_events;
     std::vector<int64_t> range_col_end;
 
@@ -371,7 +372,7 @@ static int install_blocks(itr_ctx *ctx, const uint16_t *sym, const int64_t *off,
         std::fill(chunk_blk.begin() + chunk_off[b], chunk_blk.begin() + chunk_off[b + 1], (int32_t)b);
 
     ctx->n_blocks = ctx->n_cols = ctx->n_chunks = 0;
-    ctx->have_path = ctx->have_post = false;
+    ctx->have_path = ctx->have_post = ctx->ranges_valid = false;
     // device buffers are kept across loads when they are large enough
     // (+64 columns of slack so tile prefetches past the end stay in bounds)
     CK(ensure(ctx->d_sym, ctx->cap_sym, (size_t)(n_cols + 64)));
@@ -505,7 +506,7 @@ int install_model_device(itr_ctx *ctx, int n_sets, int K, const double *d_a, con
     ctx->n_sets = n_sets;
     ctx->K = K;
     ctx->KP = KP;
-    ctx->have_path = ctx->have_post = false;
+    ctx->have_path = ctx->have_post = ctx->ranges_valid = false;
     ctx->runs_valid = false;
     if (ctx->n_blocks > 0 && K <= 32 && ctx->use_runs) {
         int prc = prepare_runs(ctx, ctx->stream);
@@ -822,7 +823,16 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const Geometry g = geometry(ctx, ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
     if (K <= 32 && (vmode ? !strcmp(vmode, "check") : ctx->use_runs)) {
-        // many chains, stable backpointers: check the cached pointer, exact scan only on a miss
+        // many chains, stable backpointers: check the cached pointer, exact scan only on a miss.
+        // One chain per warp, CTAs of four warps; at most `wps` warps per SM: more resident
+        // chains than that only stretch every chain's column latency (they share one FP64
+        // pipe) while the makespan is set by the LONGEST chain — the rest waits in the queue.
+        static const char *wenv = getenv("ITR_VCHK_WPS");          // experiments
+        const int wps = wenv ? std::max(4, atoi(wenv)) : 12;
+        Geometry g;
+        g.warps = 4;
+        g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n_blocks + 3) / 4, (int64_t)sms * (wps / 4)));
+        const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
 #define VCHK(KT) viterbi_check_kernel<KT><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
         ITR_SWITCH_KT(K, VCHK)
 #undef VCHK
@@ -1176,6 +1186,7 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
     cudaStream_t st = ctx->s_post;
     const size_t n = (size_t)ctx->n_cols * ctx->K;
     CK(cudaStreamSynchronize(st));
+    ctx->ranges_valid = false;
     CK(ensure(ctx->d_post, ctx->cap_post, n));
     if (!(ctx->K <= 32 && ctx->use_runs && ctx->runs_valid && !getenv("ITR_NO_RUNS"))) CK(ensure(ctx->d_beta, ctx->cap_beta, n));
     // forward (alpha -> d_post) on the posterior stream, backward (beta -> d_beta) on
@@ -1247,13 +1258,16 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                 // Pass 2 over contiguous ranges of blocks (input order = contiguous rows of the
                 // result): one range normally; several when the result is streamed to the host
                 // (itr_posterior_stream), each followed by an event the copy stream waits for.
-                const int n_ranges = std::max(1, std::min<int>(ctx->stream_ranges, nb));
+                // (a deferred call that keeps the result on the device may be drained by
+                // itr_posterior_stream later: give it ranges too)
+                const int want_ranges = ctx->stream_ranges > 0 ? ctx->stream_ranges : (ctx->async && !post ? 16 : 0);
+                const int n_ranges = std::max(1, std::min<int>(want_ranges, nb));
                 ctx->range_col_end.clear();
                 for (int r = 0; r < n_ranges; ++r) {
                     const int64_t b0 = (int64_t)nb * r / n_ranges, b1 = (int64_t)nb * (r + 1) / n_ranges;
                     if (b1 <= b0) continue;
                     CK(launch_post_tiles(ctx, st, b0, b1));
-                    if (ctx->stream_ranges > 0) {
+                    if (want_ranges > 0) {
                         while (ctx->range_events.size() <= ctx->range_col_end.size()) {
                             cudaEvent_t e = nullptr;
                             CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1264,6 +1278,7 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                     }
                 }
                 phase_end(ctx, ITR_PH_POST_COMBINE, st);
+                ctx->ranges_valid = want_ranges > 0;
                 if (post) {
                     CK(cudaEventRecord(ecopy, st));
                     CK(cudaStreamWaitEvent(scopy, ecopy, 0));
@@ -1429,13 +1444,18 @@ extern "C" int itr_posterior_stream(itr_ctx *ctx, double *ring, int64_t slot_col
     CK(cudaSetDevice(ctx->device));
     // Pass 2 in ranges of ~1/16 of the alignment (at least one block each), so that the
     // first rows leave the device while later ranges are still being computed.
-    const bool was_async = ctx->async;
-    ctx->async = true;
-    ctx->stream_ranges = 16;
-    rc = itr_posterior(ctx, nullptr);
-    ctx->stream_ranges = 0;
-    ctx->async = was_async;
-    if (rc) return rc;
+    // A deferred itr_posterior(ctx, NULL) that is still in flight (or just finished) is the
+    // computation that gets drained: the caller can put the posterior's kernels first, enqueue
+    // the other recursions behind them, and then start the download loop.
+    if (!(ctx->async && ctx->have_post && ctx->ranges_valid)) {
+        const bool was_async = ctx->async;
+        ctx->async = true;
+        ctx->stream_ranges = 16;
+        rc = itr_posterior(ctx, nullptr);
+        ctx->stream_ranges = 0;
+        ctx->async = was_async;
+        if (rc) return rc;
+    }
     const int K = ctx->K;
     const int64_t n_cols = ctx->n_cols;
     while ((int)ctx->grp_streams.size() < 2 * 8 + 1) {
@@ -1458,7 +1478,7 @@ extern "C" int itr_posterior_stream(itr_ctx *ctx, double *ring, int64_t slot_col
     };
     // ranges computed by the two-pass path carry events; any other path: the whole result
     // is complete when the posterior stream is (one wait)
-    const bool ranged = !ctx->range_col_end.empty() && ctx->range_col_end.back() == n_cols;
+    const bool ranged = ctx->ranges_valid && !ctx->range_col_end.empty() && ctx->range_col_end.back() == n_cols;
     if (!ranged) {
         CK(cudaEventRecord(ctx->ev_join, ctx->s_post));
         CK(cudaStreamWaitEvent(scopy, ctx->ev_join, 0));

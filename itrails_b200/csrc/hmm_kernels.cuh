@@ -1617,11 +1617,8 @@ __device__ __noinline__ ScanResult viterbi_full_column(const double *xb, const d
     return r;
 }
 
-#ifndef ITR_VCHK_MINB
-#define ITR_VCHK_MINB 2
-#endif
 template <int KT>
-__global__ void __launch_bounds__(256, ITR_VCHK_MINB)
+__global__ void __launch_bounds__(128, 4)
 viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                      const double *__restrict__ OM0, int K,
                      uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
