@@ -978,10 +978,14 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const unsigned long
         // 64 zero columns behind the alignment — valid symbols either way, results discarded)
         const uint16_t *sp = sym + col0;
         const bool first = !bwd && (w & TILE_FIRST) != 0;  // forward row at the start of a block: f_0 := pi
-        // Step s: forward rows produce column s, backward rows column 31 - s; after the DMMA the
-        // vector is multiplied by the emission of the NEXT column in the row's direction:
-        // column s itself going forward (f_s -> alpha_s), column 30 - s going backward
-        // (beta_{30-s} -> g_{30-s}).
+        // Step s: the DMMA turns x into y — forward rows: f_s = alpha_{s-1} @ a; backward rows:
+        // beta_{30-s} = g_{31-s} @ a — and x <- y * e(column c), c = s going forward (alpha_s),
+        // c = 30 - s going backward (g_{30-s} = beta_{30-s} * e_{30-s}).  Both directions park
+        // y for column c and both finish with the NEW x: going forward alpha_c * (parked
+        // beta_c), going backward g_c * (parked f_c) = f_c * e_c * beta_c — the same product.
+        // Forward parks columns 0..15 and finishes 16..31; backward parks 31 (its start
+        // vector, before the loop), 30..16 and finishes 15..0 (nothing left at s = 31); the
+        // only same-step hand-over is column 15 at s = 15.
         auto ecol = [&](int s) { return bwd ? max(PTILE - 2 - s, 0) : s; };
         double x[NQ], e[NQ];
         unsigned s_nxt = __ldg(sp + ecol(1));
@@ -990,21 +994,21 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const unsigned long
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 e[q] = __ldg(etc + (size_t)s0 * KP + 4 * q);
-                if (bwd) {   // g_31 = beta_31 * e_31
+                if (bwd) {   // beta_31 parked; g_31 = beta_31 * e_31
                     const double b31 = last ? (live[q] ? 1.0 : 0.0) : __ldg(ck_b + (size_t)g * KP + 4 * q + c);
+                    if (live[q]) alr[(PTILE - 1) * K + 4 * q] = b31;
                     x[q] = b31 * __ldg(etc + (size_t)s31 * KP + 4 * q);
                 } else {
                     x[q] = __ldg(ck_a + (size_t)g * KP + 4 * q + c);      // alpha_{-1} (tile 0 of a block: unused slot, finite)
                 }
             }
         }
-        // one step; v = the vector this row hands over for its column
-        auto advance = [&](int s, double (&v)[NQ]) {
+        // one step: y = x @ a (handed back for parking), x = y * e
+        auto advance = [&](int s, double (&y)[2 * NC]) {
             const unsigned s_n2 = __ldg(sp + ecol(s + 2));
             double en[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) en[q] = __ldg(etc + (size_t)s_nxt * KP + 4 * q);
-            double y[2 * NC];
 #pragma unroll
             for (int j = 0; j < 2 * NC; ++j) y[j] = 0.0;
 #pragma unroll
@@ -1016,49 +1020,60 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const unsigned long
                 for (int q = 0; q < NQ; ++q) y[q] = pi0[q];
             }
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                v[q] = bwd ? x[q] : y[q];
-                x[q] = y[q] * e[q];
-            }
+            for (int q = 0; q < NQ; ++q) x[q] = y[q] * e[q];
             if ((s & 7) == 7) quad_rescale<NQ>(x);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) e[q] = en[q];
             s_nxt = s_n2;
         };
+        auto park = [&](double *slot, const double (&y)[2 * NC], bool on) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (on && live[q]) slot[4 * q] = y[q];
+        };
+        // posterior row of the slot's column: (parked vector of the other direction) * x, normalised
+        auto finish = [&](double *slot, bool on) {
+            double p[NQ], ps[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                p[q] = (on && live[q]) ? slot[4 * q] * x[q] : 0.0;
+                ps[q & 3] += p[q];
+            }
+            double sum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            sum += __shfl_xor_sync(FULL, sum, 1);
+            sum += __shfl_xor_sync(FULL, sum, 2);
+            const double inv = 1.0 / sum;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (on && live[q]) slot[4 * q] = p[q] * inv;
+        };
         {
-            double *slot = alr + (bwd ? (PTILE - 1) * K : 0);
+            double *slot = alr + (bwd ? (PTILE - 2) * K : 0);   // column 0 going forward, 30 going backward
             const int dslot = bwd ? -K : K;
 #pragma unroll MMA_UNROLL
-            for (int s = 0; s < HALF; ++s) {              // park f_s / g_{31-s}
-                double v[NQ];
-                advance(s, v);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    if (live[q]) slot[4 * q] = v[q];
+            for (int s = 0; s < HALF - 1; ++s) {          // park columns 0..14 / 30..16
+                double y[2 * NC];
+                advance(s, y);
+                park(slot, y, true);
                 slot += dslot;
             }
-            __syncwarp();                                 // the other direction's first 16 vectors are parked
+            {                                             // s = 15: forward parks column 15, backward finishes it
+                double y[2 * NC];
+                advance(HALF - 1, y);
+                park(slot, y, !bwd);
+                __syncwarp();                             // every parked vector is visible from here on
+                finish(slot, bwd);
+                slot += dslot;
+            }
             if (c == 0) {                                 // next group's symbols (its tile word has arrived by now)
                 const uint16_t *ns = sym + (w_next & TILE_COL_MASK);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ns));
             }
 #pragma unroll MMA_UNROLL
-            for (int s = HALF; s < PTILE; ++s) {          // meet the parked vector: posterior row, normalised
-                double v[NQ];
-                advance(s, v);
-                double p[NQ], ps[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    p[q] = live[q] ? slot[4 * q] * v[q] : 0.0;
-                    ps[q & 3] += p[q];
-                }
-                double sum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-                sum += __shfl_xor_sync(FULL, sum, 1);
-                sum += __shfl_xor_sync(FULL, sum, 2);
-                const double inv = 1.0 / sum;
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    if (live[q]) slot[4 * q] = p[q] * inv;
+            for (int s = HALF; s < PTILE; ++s) {          // finish columns 16..31 / 14..0
+                double y[2 * NC];
+                advance(s, y);
+                finish(slot, !bwd || s < PTILE - 1);
                 slot += dslot;
             }
         }
@@ -1618,7 +1633,7 @@ __device__ __noinline__ ScanResult viterbi_full_column(const double *xb, const d
 }
 
 template <int KT>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                      const double *__restrict__ OM0, int K,
                      uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
@@ -1698,7 +1713,7 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
         };
         int64_t t0 = 0;
         for (; t0 + 32 < T; t0 += 32) {
-#pragma unroll UNROLL_VIT
+#pragma unroll 2
             for (int s32 = 0; s32 < 32; ++s32) column(s32);
             vcur = vnxt;
             vnxt = st.load(t0 + 64, lane);

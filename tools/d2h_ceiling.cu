@@ -86,9 +86,7 @@ int main(int argc, char **argv) {
     const char *sep = "";
     struct Cfg { const char *name; size_t piece; int slots; unsigned flags; bool ring; } cfgs[] = {
         {"ring_4x256MiB", 256ull << 20, 4, cudaHostAllocDefault, true},
-        {"ring_4x64MiB", 64ull << 20, 4, cudaHostAllocDefault, true},
         {"ring_4x256MiB_write_combined", 256ull << 20, 4, cudaHostAllocWriteCombined, true},
-        {"whole_buffer_256MiB_pieces", 256ull << 20, 4, cudaHostAllocDefault, false},
     };
     for (const Cfg &c : cfgs) {
         printf("%s \"%s\": {", sep, c.name);
