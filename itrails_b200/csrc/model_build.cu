@@ -71,7 +71,7 @@ constexpr double THETA13 = 5.371920351148152;
 template <int NT>
 struct ExpmCfg {
     static constexpr int NP = 8 * NT, LD = NP + 4, NTHR = 32 * NT;
-    static constexpr size_t SMEM = (size_t)(2 * NP * LD + 3 * NP) * sizeof(double) + 16;
+    static constexpr size_t SMEM = (size_t)(2 * NP * LD + 3 * NP) * sizeof(double) + (4 + 2 * NP) * sizeof(int);
 };
 
 template <int NT>
@@ -186,49 +186,93 @@ expm_kernel(const ExpmTask *__restrict__ tasks, int n_tasks, const DevGen *__res
         gemm_strip<NT>(X, Y, acc, warp, lane);
         store(SV, true, PADE13[6], PADE13[4], PADE13[2], PADE13[0]);
         __syncthreads();
-        // ---- solve (V - U) R = (V + U): Gauss-Jordan with partial pivoting, X = V-U, Y = V+U
-        for (int e = tid; e < NN; e += NTHR) {
-            const double u = SU[e], v = SV[e];
-            X[(e / NP) * LD + (e % NP)] = v - u;
-            Y[(e / NP) * LD + (e % NP)] = v + u;
-        }
-        __syncthreads();
-        for (int k = 0; k < NP; ++k) {
-            if (warp == 0) {
-                double best = -1.0;
-                int bi = k;
-                for (int i = k + lane; i < NP; i += 32) {
-                    const double v = fabs(X[i * LD + k]);
-                    if (v > best) { best = v; bi = i; }
-                }
+        // ---- solve (V - U) R = (V + U): Gauss-Jordan with partial pivoting on the augmented
+        // NP x 2NP matrix [V-U | V+U], held in REGISTERS: thread (rg, cg) = (tid / 16, tid % 16)
+        // owns rows 4rg..4rg+3 and columns cg + 16m (m < NT).  Per pivot: the owners of column k
+        // publish it, warp 0 picks the pivot among the rows not used yet (implicit pivoting: rows
+        // never move, the permutation is applied when the result is written back), the owners
+        // of the pivot row publish it scaled, everybody updates its 4 x NT block with register
+        // FMAs.  Three barriers and ~4 NT FMAs per thread and pivot.
+        {
+            double v[4][NT];
+            const int rg = tid >> 4, cg = tid & 15;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int m = 0; m < NT; ++m) {
+                    const int i = 4 * rg + a, j = cg + 16 * m, e = i * NP + (j < NP ? j : j - NP);
+                    const double u = SU[e], w = SV[e];
+                    v[a][m] = j < NP ? w - u : w + u;
                 }
-                if (lane == 0) misc[0] = bi;
+            int *used = misc + 4, *where = used + NP;          // row used as pivot? / where[k] = pivot row of column k
+            for (int i = tid; i < NP; i += NTHR) used[i] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int mk = 0; mk < (NP + 15) / 16; ++mk) {
+#pragma unroll 1
+                for (int kk = 0; kk < 16 && 16 * mk + kk < NP; ++kk) {
+                    const int k = 16 * mk + kk;
+                    if (cg == kk) {                        // column k: cg == k % 16, register slot mk
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) fcol[4 * rg + a] = v[a][mk];
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        double best = -1.0;
+                        int bi = 0x7fffffff;
+                        for (int i = lane; i < NP; i += 32) {
+                            const double c = used[i] ? -1.0 : fabs(fcol[i]);
+                            if (c > best) { best = c; bi = i; }
+                        }
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) {
+                            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                        }
+                        if (lane == 0) { misc[0] = bi; used[bi] = 1; where[k] = bi; }
+                    }
+                    __syncthreads();
+                    const int p = misc[0];
+                    if (rg == (p >> 2)) {                  // pivot row, scaled by 1 / pivot
+                        const double inv = 1.0 / fcol[p];
+                        const int a = p & 3;
+#pragma unroll
+                        for (int m = 0; m < NT; ++m) {
+                            const double x = a == 0 ? v[0][m] : a == 1 ? v[1][m] : a == 2 ? v[2][m] : v[3][m];
+                            prow[cg + 16 * m] = x * inv;
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int i = 4 * rg + a;
+                        const double f = fcol[i];
+                        const bool piv = i == p;
+#pragma unroll
+                        for (int m = 0; m < NT; ++m) {
+                            const double pr = prow[cg + 16 * m];
+                            v[a][m] = piv ? pr : fma(-f, pr, v[a][m]);
+                        }
+                    }
+                    // (fcol / prow are rewritten only after the next barrier)
+                }
             }
             __syncthreads();
-            const int p = misc[0];
-            const double inv = 1.0 / X[p * LD + k];
-            for (int j = tid; j < 2 * NP; j += NTHR) prow[j] = (j < NP ? X[p * LD + j] : Y[p * LD + j - NP]) * inv;
-            for (int i = tid; i < NP; i += NTHR) fcol[i] = X[i * LD + k];
+            // row where[k] now holds row k of the solution in its right half: Y <- R
+#pragma unroll
+            for (int a = 0; a < 4; ++a) fcol[4 * rg + a] = 0.0;   // (reuse as scratch is not needed; keep the barrier pattern simple)
             __syncthreads();
-            const double fk = fcol[k];     // factor of the row that moves into position p
-            for (int e = tid; e < NP * 2 * NP; e += NTHR) {
-                const int i = e / (2 * NP), j = e % (2 * NP);
-                if (i == p && p != k) continue;            // written by the thread that owns (k, j)
-                double *cell = (j < NP) ? &X[i * LD + j] : &Y[i * LD + j - NP];
-                const double pr = prow[j];
-                if (i == k) {
-                    if (p != k) {
-                        double *cp = (j < NP) ? &X[p * LD + j] : &Y[p * LD + j - NP];
-                        *cp = *cell - fk * pr;             // old row k lands in row p, eliminated
-                    }
-                    *cell = pr;
-                } else {
-                    *cell -= fcol[i] * pr;
+            int *rowof = used;                             // rowof[i] = k with where[k] == i
+            for (int k = tid; k < NP; k += NTHR) rowof[where[k]] = k;
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int kr = rowof[4 * rg + a];
+#pragma unroll
+                for (int m = 0; m < NT; ++m) {
+                    const int j = cg + 16 * m;
+                    if (j >= NP) Y[kr * LD + j - NP] = v[a][m];
                 }
             }
             __syncthreads();
