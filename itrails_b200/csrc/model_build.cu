@@ -71,7 +71,7 @@ constexpr double THETA13 = 5.371920351148152;
 template <int NT>
 struct ExpmCfg {
     static constexpr int NP = 8 * NT, LD = NP + 4, NTHR = 32 * NT;
-    static constexpr size_t SMEM = (size_t)(2 * NP * LD + 3 * NP) * sizeof(double) + (4 + 2 * NP) * sizeof(int);
+    static constexpr size_t SMEM = (size_t)(2 * NP * LD + 9 * NP) * sizeof(double) + (4 + 2 * NP) * sizeof(int);
 };
 
 template <int NT>
@@ -98,8 +98,8 @@ expm_kernel(const ExpmTask *__restrict__ tasks, int n_tasks, const DevGen *__res
     using C = ExpmCfg<NT>;
     constexpr int NP = C::NP, LD = C::LD, NTHR = C::NTHR, NN = NP * NP;
     extern __shared__ __align__(16) double sm[];
-    double *X = sm, *Y = sm + NP * LD, *prow = Y + NP * LD, *fcol = prow + 2 * NP;
-    int *misc = reinterpret_cast<int *>(fcol + NP);
+    double *X = sm, *Y = sm + NP * LD, *prow = Y + NP * LD, *fcol = prow + 2 * NP;   // prow[2NP]; fcol: 7 NP doubles (norms, then the solve's buffers)
+    int *misc = reinterpret_cast<int *>(fcol + 7 * NP);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     double *SA = ws + (size_t)blockIdx.x * 7 * NN, *S2 = SA + NN, *S4 = S2 + NN, *S6 = S4 + NN, *SW = S6 + NN,
@@ -189,10 +189,13 @@ expm_kernel(const ExpmTask *__restrict__ tasks, int n_tasks, const DevGen *__res
         // ---- solve (V - U) R = (V + U): Gauss-Jordan with partial pivoting on the augmented
         // NP x 2NP matrix [V-U | V+U], held in REGISTERS: thread (rg, cg) = (tid / 16, tid % 16)
         // owns rows 4rg..4rg+3 and columns cg + 16m (m < NT).  Per pivot: the owners of column k
-        // publish it, warp 0 picks the pivot among the rows not used yet (implicit pivoting: rows
-        // never move, the permutation is applied when the result is written back), the owners
-        // of the pivot row publish it scaled, everybody updates its 4 x NT block with register
-        // FMAs.  Three barriers and ~4 NT FMAs per thread and pivot.
+        // publish it; EVERY warp finds the pivot among the rows not used yet (same answer in
+        // every warp, so no broadcast and no serial section; implicit pivoting: rows never
+        // move, the permutation is applied when the result is written back); the owners of
+        // the pivot row publish it as it is; everybody subtracts (column entry / pivot) times
+        // that row from its 4 x NT block with register FMAs — the pivot row itself with
+        // multiplier 0, so it is never rescaled in place: row where[k] is divided by its
+        // pivot once, at the end.  Two barriers per pivot (publications are double buffered).
         {
             double v[4][NT];
             const int rg = tid >> 4, cg = tid & 15;
@@ -204,75 +207,65 @@ expm_kernel(const ExpmTask *__restrict__ tasks, int n_tasks, const DevGen *__res
                     const double u = SU[e], w = SV[e];
                     v[a][m] = j < NP ? w - u : w + u;
                 }
-            int *used = misc + 4, *where = used + NP;          // row used as pivot? / where[k] = pivot row of column k
-            for (int i = tid; i < NP; i += NTHR) used[i] = 0;
-            __syncthreads();
+            double *fc2 = fcol, *pr2 = fcol + 2 * NP, *pv = pr2 + 4 * NP;   // fcol[2][NP], prow[2][2NP], pivot values [NP]
+            int *where = misc + 4, *rowof = where + NP;        // where[k] = pivot row of column k
+            unsigned usedbits = 0;                             // bit b: row lane + 32 b has been a pivot (same in every warp)
 #pragma unroll
             for (int mk = 0; mk < (NP + 15) / 16; ++mk) {
 #pragma unroll 1
                 for (int kk = 0; kk < 16 && 16 * mk + kk < NP; ++kk) {
                     const int k = 16 * mk + kk;
+                    double *fc = fc2 + (k & 1) * NP, *pw = pr2 + (k & 1) * 2 * NP;
                     if (cg == kk) {                        // column k: cg == k % 16, register slot mk
 #pragma unroll
-                        for (int a = 0; a < 4; ++a) fcol[4 * rg + a] = v[a][mk];
+                        for (int a = 0; a < 4; ++a) fc[4 * rg + a] = v[a][mk];
                     }
                     __syncthreads();
-                    if (warp == 0) {
-                        double best = -1.0;
-                        int bi = 0x7fffffff;
-                        for (int i = lane; i < NP; i += 32) {
-                            const double c = used[i] ? -1.0 : fabs(fcol[i]);
-                            if (c > best) { best = c; bi = i; }
-                        }
+                    double best = -1.0;
+                    int p = 0x7fffffff;
 #pragma unroll
-                        for (int o = 16; o; o >>= 1) {
-                            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                        }
-                        if (lane == 0) { misc[0] = bi; used[bi] = 1; where[k] = bi; }
+                    for (int b = 0; b < (NP + 31) / 32; ++b) {
+                        const int i = lane + 32 * b;
+                        const double cnd = (i < NP && !((usedbits >> b) & 1u)) ? fabs(fc[i]) : -1.0;
+                        if (cnd > best) { best = cnd; p = i; }
                     }
-                    __syncthreads();
-                    const int p = misc[0];
-                    if (rg == (p >> 2)) {                  // pivot row, scaled by 1 / pivot
-                        const double inv = 1.0 / fcol[p];
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, p, o);
+                        if (ob > best || (ob == best && oi < p)) { best = ob; p = oi; }
+                    }
+                    if ((p & 31) == lane) usedbits |= 1u << (p >> 5);
+                    const double pivot = fc[p], inv = 1.0 / pivot;
+                    if (tid == 0) { where[k] = p; pv[k] = pivot; }
+                    if (rg == (p >> 2)) {                  // the pivot row as it is
                         const int a = p & 3;
 #pragma unroll
-                        for (int m = 0; m < NT; ++m) {
-                            const double x = a == 0 ? v[0][m] : a == 1 ? v[1][m] : a == 2 ? v[2][m] : v[3][m];
-                            prow[cg + 16 * m] = x * inv;
-                        }
+                        for (int m = 0; m < NT; ++m)
+                            pw[cg + 16 * m] = a == 0 ? v[0][m] : a == 1 ? v[1][m] : a == 2 ? v[2][m] : v[3][m];
                     }
                     __syncthreads();
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int i = 4 * rg + a;
-                        const double f = fcol[i];
-                        const bool piv = i == p;
+                        const double mult = i == p ? 0.0 : fc[i] * inv;
 #pragma unroll
-                        for (int m = 0; m < NT; ++m) {
-                            const double pr = prow[cg + 16 * m];
-                            v[a][m] = piv ? pr : fma(-f, pr, v[a][m]);
-                        }
+                        for (int m = 0; m < NT; ++m) v[a][m] = fma(-mult, pw[cg + 16 * m], v[a][m]);
                     }
-                    // (fcol / prow are rewritten only after the next barrier)
                 }
             }
             __syncthreads();
-            // row where[k] now holds row k of the solution in its right half: Y <- R
-#pragma unroll
-            for (int a = 0; a < 4; ++a) fcol[4 * rg + a] = 0.0;   // (reuse as scratch is not needed; keep the barrier pattern simple)
-            __syncthreads();
-            int *rowof = used;                             // rowof[i] = k with where[k] == i
+            // row where[k], divided by its pivot, is row k of the solution in its right half: Y <- R
             for (int k = tid; k < NP; k += NTHR) rowof[where[k]] = k;
             __syncthreads();
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int kr = rowof[4 * rg + a];
+                const double inv = 1.0 / pv[kr];
 #pragma unroll
                 for (int m = 0; m < NT; ++m) {
                     const int j = cg + 16 * m;
-                    if (j >= NP) Y[kr * LD + j - NP] = v[a][m];
+                    if (j >= NP) Y[kr * LD + j - NP] = v[a][m] * inv;
                 }
             }
             __syncthreads();
@@ -335,44 +328,91 @@ absorb_kernel(const double *__restrict__ scal, int scal_stride, const DevGen *__
         M[tr * W + nT] = rhs;
     }
     __syncthreads();
-    for (int k = 0; k < nT; ++k) {
-        if (tid < 32) {
+    // Gauss-Jordan on [M | rhs] (nT x (nT + 1)) in registers, as in expm_kernel: thread
+    // (rg, cg) = (tid / 16, tid % 16) owns rows 9rg..9rg+8 and columns cg + 16m (m < 5); every
+    // warp finds the pivot among the rows not used yet (implicit pivoting), the pivot row is
+    // published as it is, two barriers per pivot.  The solution entry of the pivot row of
+    // column k is its last column divided by its pivot.
+    constexpr int RPT = AB_MAXT / 8, CPT = (AB_MAXT + 1 + 15) / 16;
+    double v[RPT][CPT];
+    const int rg = tid >> 4, cg = tid & 15, lane = tid & 31;
+#pragma unroll
+    for (int a = 0; a < RPT; ++a)
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) {
+            const int i = RPT * rg + a, j = cg + 16 * m;
+            v[a][m] = (i < nT && j < W) ? M[i * W + j] : 0.0;
+        }
+    __syncthreads();                                   // M is reused below as publication space
+    double *fc2 = M, *pr2 = M + 2 * AB_MAXT, *sol = pr2 + 2 * 16 * CPT, *pvs = sol + AB_MAXT;   // fcol[2][72], prow[2][80], solution [72], pivots [72]
+    int *where = reinterpret_cast<int *>(pvs + AB_MAXT);
+    unsigned usedbits = 0;
+#pragma unroll
+    for (int mk = 0; mk < (AB_MAXT + 15) / 16; ++mk) {
+#pragma unroll 1
+        for (int kk = 0; kk < 16 && 16 * mk + kk < nT; ++kk) {
+            const int k = 16 * mk + kk;
+            double *fc = fc2 + (k & 1) * AB_MAXT, *pw = pr2 + (k & 1) * 16 * CPT;
+            if (cg == kk) {
+#pragma unroll
+                for (int a = 0; a < RPT; ++a) fc[RPT * rg + a] = v[a][mk];
+            }
+            __syncthreads();
             double best = -1.0;
-            int bi = k;
-            for (int i = k + tid; i < nT; i += 32) {
-                const double v = fabs(M[i * W + k]);
-                if (v > best) { best = v; bi = i; }
+            int p = 0x7fffffff;
+#pragma unroll
+            for (int b = 0; b < (AB_MAXT + 31) / 32; ++b) {
+                const int i = lane + 32 * b;
+                const double cnd = (i < nT && !((usedbits >> b) & 1u)) ? fabs(fc[i]) : -1.0;
+                if (cnd > best) { best = cnd; p = i; }
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                const int oi = __shfl_xor_sync(0xffffffffu, p, o);
+                if (ob > best || (ob == best && oi < p)) { best = ob; p = oi; }
             }
-            if (tid == 0) pivot = bi;
-        }
-        __syncthreads();
-        const int p = pivot;
-        const double inv = 1.0 / M[p * W + k];
-        for (int j = tid; j < W; j += blockDim.x) prow[j] = M[p * W + j] * inv;
-        for (int i = tid; i < nT; i += blockDim.x) fcol[i] = M[i * W + k];
-        __syncthreads();
-        const double fk = fcol[k];
-        for (int e = tid; e < nT * W; e += blockDim.x) {
-            const int i = e / W, j = e % W;
-            if (i == p && p != k) continue;
-            const double pr = prow[j];
-            if (i == k) {
-                if (p != k) M[p * W + j] = M[k * W + j] - fk * pr;
-                M[k * W + j] = pr;
-            } else {
-                M[i * W + j] -= fcol[i] * pr;
+            if ((p & 31) == lane) usedbits |= 1u << (p >> 5);
+            const double inv = 1.0 / fc[p];
+            if (tid == 0) { where[k] = p; pvs[k] = fc[p]; }
+            if (rg == p / RPT) {
+                const int a = p - RPT * rg;
+#pragma unroll
+                for (int m = 0; m < CPT; ++m) {
+                    double x = v[0][m];
+#pragma unroll
+                    for (int q = 1; q < RPT; ++q) x = a == q ? v[q][m] : x;
+                    pw[cg + 16 * m] = x;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < RPT; ++a) {
+                const int i = RPT * rg + a;
+                const double mult = i == p ? 0.0 : fc[i] * inv;
+#pragma unroll
+                for (int m = 0; m < CPT; ++m) v[a][m] = fma(-mult, pw[cg + 16 * m], v[a][m]);
             }
         }
+    }
+    // The pivot row of column k, divided by the pivot it had when it was chosen, is row k of
+    // the reduced system: w_k = (its last column) / pivot_k.
+    __syncthreads();
+    {
+        const int mlast = nT / 16, clast = nT % 16;            // the right-hand side: column nT = slot mlast of cg == clast
+        double *rhsv = fc2;                                    // [72], indexed by row
+#pragma unroll
+        for (int m = 0; m < CPT; ++m)
+            if (m == mlast && cg == clast) {
+#pragma unroll
+                for (int a = 0; a < RPT; ++a) rhsv[RPT * rg + a] = v[a][m];
+            }
+        __syncthreads();
+        for (int k = tid; k < nT; k += blockDim.x) sol[k] = rhsv[where[k]] / pvs[k];
         __syncthreads();
     }
     double *out = absorb + ((size_t)set * 9 + xy) * NP3;
-    for (int r = tid; r < NP3; r += blockDim.x) out[r] = (r < gn.n && rank[r] >= 0) ? M[rank[r] * W + nT] : 0.0;
+    for (int r = tid; r < NP3; r += blockDim.x) out[r] = (r < gn.n && rank[r] >= 0) ? M[2 * AB_MAXT + 2 * 16 * ((AB_MAXT + 1 + 15) / 16) + rank[r]] : 0.0;
 }
 
 // ---------------------------------------------------------------------------------
