@@ -757,14 +757,13 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     ctx->launches += 1;
     // Few chains: four warps per chain (latency); many chains: one warp per chain (throughput).
     const int sms = ctx->prop.multiProcessorCount;
-    const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "stream", "spec", "4warp", "1warp"
+    const char *vmode = getenv("ITR_VITERBI");          // experiments / tests: "stream", "check", "4warp" (and ITR_VITERBI_1WARP)
     // (speculation pays when backpointers are stable, i.e. on alignments dominated by a few
     // symbols — the same test that enables run compression; else every window mispredicts)
     // (up to ~3 chains per SM the decoupled sweep, one CTA per chain pulled longest-first from
     // the queue, beats one warp per chain: 133 against ~360 cycles per column)
-    const bool want_spec = vmode ? (!strcmp(vmode, "spec") || !strcmp(vmode, "stream")) : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms);
-    const bool want_stream = vmode ? !strcmp(vmode, "stream") : true;      // ("spec": the windowed predecessor)
-    if (K <= 32 && want_spec && want_stream && ctx->max_T < 0x7fffffff) {
+    const bool want_stream = vmode ? !strcmp(vmode, "stream") : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms);
+    if (K <= 32 && want_stream && ctx->max_T < 0x7fffffff) {
         // decoupled speculate-and-verify sweep: runner, feeder and 14 verifiers per chain
         const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);
         const size_t shs = (size_t)(NSYM * 32 + 2 * STR_R * 32) * sizeof(double) + (size_t)STR_R * 32;
@@ -785,29 +784,6 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
             default: VSTR(32); break;
         }
 #undef VSTR
-        return;
-    }
-    if (K <= 32 && want_spec && !getenv("ITR_VITERBI_1WARP")) {
-        // speculate-and-verify sweep: one CTA of 16 warps per chain
-        const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);
-        const size_t shs = (size_t)NSYM * 32 * sizeof(double);
-#define VSPEC(KT)                                                                                             \
-    do {                                                                                                      \
-        cudaFuncSetAttribute(viterbi_spec_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shs); \
-        viterbi_spec_kernel<KT><<<grid, 32 * SPEC_NW, shs, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K,    \
-                                                                 ctx->d_bp, ctx->d_final);                    \
-    } while (0)
-        switch ((K + 3) / 4) {
-            case 1: VSPEC(4); break;
-            case 2: VSPEC(8); break;
-            case 3: VSPEC(12); break;
-            case 4: VSPEC(16); break;
-            case 5: VSPEC(20); break;
-            case 6: VSPEC(24); break;
-            case 7: VSPEC(28); break;
-            default: VSPEC(32); break;
-        }
-#undef VSPEC
         return;
     }
     if (K <= 32 && (vmode ? !strcmp(vmode, "4warp") : ctx->n_blocks <= (int64_t)4 * sms) && !getenv("ITR_VITERBI_1WARP")) {

@@ -1924,213 +1924,22 @@ __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, do
 }
 
 // ---------------------------------------------------------------------------------
-// Viterbi forward sweep by speculation and exact verification (K <= 32, few chains).
+// Viterbi forward sweep by speculation and exact verification, DECOUPLED (K <= 32, few chains).
 //
 // Measured on the (3,3) model: the vector of backpointers changes in only 1.7 % of the
-// columns (mean stable stretch 55 columns; 90 % of the pointers are "stay").  So a CTA
-// of SPEC_NW warps walks one chain in windows of SPEC_W columns:
-//   1. warp 0 runs the window speculatively with the cached pointers p_j: omega_j =
-//      (omega_{p_j} + log a_{p_j j}) + log e_j — two exactly-rounded adds and one
-//      shared-memory gather per column instead of a K-way argmax on the dependent chain;
-//   2. all warps verify the window's columns in parallel, each with the full exact scan
-//      (tournament + hoisting check + literal fallback, as in viterbi_forward_kernel)
-//      from the speculative omega of the column before;
-//   3. columns before the first mismatch are committed (verified: same adds, same first
-//      maximiser as the reference); the mismatching column takes the verifier's result,
-//      the pointers are updated, and the next window starts right after it.
-// Results are bit-identical to the sequential sweep by induction over committed columns.
-// ---------------------------------------------------------------------------------
-constexpr int SPEC_W = 15, SPEC_NW = 16;       // warp 0 runs ahead, warps 1..15 verify one column each
-
-template <int KT>
-__global__ void __launch_bounds__(32 * SPEC_NW)
-viterbi_spec_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
-                    const double *__restrict__ OM0, int K,
-                    uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
-    constexpr int KP = 32, W = SPEC_W;
-    // Two windows in flight: while the verifiers check the pending window (buffer pb), the
-    // runner speculates the window after it into the other buffer; that speculation is
-    // dropped if the pending window turns out to hold a mismatch.
-    __shared__ __align__(16) double wom[2][W + 1][KP];  // omega before column i of a window (speculative for i > 0)
-    __shared__ __align__(16) double rom[W][KP];         // verified omega of column i of the pending window
-    __shared__ int rarg[W][KP];                         // verified first arg-maxima
-    __shared__ int mism[2][W];                          // column i differs from the runner's choice (by step parity)
-    __shared__ int wsym[2][W];                          // symbols of the windows
-    __shared__ int wptr[2][W][KP];                      // the pointer the runner chose for each column
-    __shared__ double las[KP][KP];                      // log a, for the runner's pointer lookups
-    __shared__ int chain_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_chains = cs.n_blocks;
-    const int K4 = (K + 3) & ~3;
-    // the whole log-emission table lives in shared memory (625 x 32 doubles = 160 KB): with one
-    // CTA per SM the L1 left over is too small to keep the rows resident, and every lookup
-    // of the runner would otherwise pay an L2 round trip
-    extern __shared__ __align__(16) double les[];
-    for (int e = threadIdx.x; e < NSYM * KP; e += blockDim.x) les[e] = __ldg(LEt + e);
-    const double *etl = les + lane;
-    Cols<KT, 1, true> lacol;                            // column `lane` of log a (verifiers)
-    if (warp > 0) lacol.load(LA, KP, lane);
-    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) las[e / KP][e % KP] = __ldg(LA + e);
-    __syncthreads();
-
-    for (;;) {
-        if (threadIdx.x == 0) chain_s = (int)atomicAdd(cs.queue, 1u);
-        __syncthreads();
-        const int c = chain_s;
-        __syncthreads();
-        if (c >= n_chains) break;
-        const int blk = cs.order[c];
-        const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
-        const uint16_t *symp = cs.sym + beg;            // (64 columns of slack behind the last block)
-        uint8_t *bpl = bp + (size_t)beg * KP + lane;
-
-        // runner state (warp 0): per state its two most recent predecessors, kept sorted by
-        // index (lo <= hi) with their log a entries.  Mispredictions come mostly from states
-        // flipping back to their previous predecessor (measured: 335 -> 53 per 20 000 columns
-        // when the runner takes the better of the two), so the runner evaluates both; with the
-        // pair sorted, "hi wins only if strictly greater" is np.argmax's first-maximum rule.
-        int lo = lane, hi = lane;
-        double la_lo = __ldg(LA + (size_t)lane * KP + lane), la_hi = la_lo;
-        // symbols of the window the runner will most likely speculate next (the one right
-        // after the window it is speculating now), fetched a step ahead; reloaded after a mismatch
-        int64_t pre_ts = 1;
-        unsigned pre_sym = 0;
-        if (warp == 0) {
-            wom[0][0][lane] = __ldg(OM0 + (size_t)blk * KP + lane);
-            pre_sym = (unsigned)__ldg(symp + 1 + lane);
-        }
-        int64_t tp = 1;                                  // first column not yet committed
-        int pb = 0, np_ = 0;                             // pending window: buffer, length (columns tp .. tp+np_-1)
-        int fin_b = 0, fin_i = 0;                        // where the last committed omega lives
-        int par = 0;                                     // step parity (double-buffers `mism`)
-        __syncthreads();
-        while (tp < T) {
-            const int sb = np_ ? pb ^ 1 : pb;            // buffer the runner speculates into
-            const int64_t ts = tp + np_;                 // first column of that window
-            const int ns = (int)max((int64_t)0, min((int64_t)W, T - ts));
-            int myp = 0;
-            if (warp == 0) {
-                // ---- runner: omega_j = (omega_{p_j} + log a_{p_j j}) + log e_j along the window
-                if (ns > 0) {
-                    const unsigned mysym = (pre_ts == ts) ? pre_sym : (unsigned)__ldg(symp + ts + lane);
-                    if (lane < W) wsym[sb][lane] = (int)mysym;
-                    if (np_) wom[sb][0][lane] = wom[pb][np_][lane];   // continue from the pending window's (speculative) end
-                    __syncwarp();
-                    // the symbols of the window after this one: the load lands during the loop below
-                    pre_ts = ts + ns;
-                    pre_sym = (unsigned)__ldg(symp + pre_ts + lane);
-                    double ew[W];
-#pragma unroll
-                    for (int i = 0; i < W; ++i) ew[i] = etl[wsym[sb][i] * KP];
-                    // (shared-memory gathers: a 64-bit shuffle costs ~2 x 16 issue cycles on this part)
-                    const double *wlo = &wom[sb][0][lo], *whi = &wom[sb][0][hi];
-                    double xl = wlo[0], xh = whi[0];
-#pragma unroll
-                    for (int i = 0; i < W; ++i) {
-                        if (i < ns) {
-                            const double s_l = __dadd_rn(xl, la_lo), s_h = __dadd_rn(xh, la_hi);
-                            const bool take = s_h > s_l;    // (the verifier has the last word)
-                            const double M = __dadd_rn(take ? s_h : s_l, ew[i]);
-                            wom[sb][i + 1][lane] = M;      // for the verifiers and for the next column
-                            wptr[sb][i][lane] = take ? hi : lo;
-                            __syncwarp();
-                            xl = wlo[(i + 1) * KP];         // omega of the two candidate predecessors
-                            xh = whi[(i + 1) * KP];
-                        }
-                    }
-                }
-            } else if (warp - 1 < np_) {
-                // ---- verifiers: exact scan of column (warp - 1) of the pending window
-                const int i = warp - 1;
-                myp = wptr[pb][i][lane];
-                const double le = etl[wsym[pb][i] * KP];
-                const double2 *x2 = reinterpret_cast<const double2 *>(&wom[pb][i][0]);
-                double sv[KT];
-                int ix[KT];
-#pragma unroll
-                for (int q = 0; q < KT; q += 2) {
-                    const double2 pq = x2[q / 2];
-                    sv[q] = __dadd_rn(pq.x, lacol.get(0, q));
-                    sv[q + 1] = __dadd_rn(pq.y, lacol.get(0, q + 1));
-                    ix[q] = q;
-                    ix[q + 1] = q + 1;
-                }
-                tournament<KT>(sv, ix);
-                double M = __dadd_rn(sv[0], le);
-                int arg = ix[0];
-                if (__any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(sv[0], le, M))) {
-                    const ScanResult r = viterbi_exact_scan(&wom[pb][i][0], LA + lane, KP, K4, le);
-                    M = r.best;
-                    arg = r.arg;
-                }
-                rom[i][lane] = M;
-                rarg[i][lane] = arg;
-                const bool bad = __any_sync(FULL, (lane < K) & (arg != myp));
-                if (lane == 0) mism[par][i] = bad ? 1 : 0;
-            }
-            __syncthreads();
-            // ---- everyone: first mismatching column of the pending window (np_ if none); commit
-            const unsigned bad = __ballot_sync(FULL, lane < np_ && mism[par][lane]);
-            par ^= 1;
-            const int f = bad ? __ffs(bad) - 1 : np_;
-            if (warp > 0 && warp - 1 < f) bpl[(size_t)(tp + warp - 1) * KP] = (uint8_t)myp;
-            if (f < np_) {
-                // mismatch: column f takes the verifier's result; the speculation beyond it is dropped
-                if (warp == 0) {
-                    const int np2 = rarg[f][lane], chosen = wptr[pb][f][lane];
-                    // new candidate pair: the verified predecessor and the most recent other one
-                    const int other = (chosen != np2) ? chosen : (lo != np2) ? lo : hi;
-                    lo = min(np2, other);
-                    hi = max(np2, other);
-                    la_lo = las[lo][lane];
-                    la_hi = las[hi][lane];
-                    bpl[(size_t)(tp + f) * KP] = (uint8_t)np2;
-                    wom[0][0][lane] = rom[f][lane];
-                }
-                tp += f + 1;
-                pb = 0;
-                np_ = 0;
-                fin_b = 0;
-                fin_i = 0;
-            } else {
-                if (np_) {
-                    fin_b = pb;
-                    fin_i = np_;
-                }
-                tp += np_;
-                pb = sb;
-                np_ = ns;
-            }
-            // One barrier per step suffices: what the next step writes (the other window
-            // buffer, `mism` of the other parity, rom/rarg only when a window is pending) is
-            // never read again by this one, and after a mismatch the verifiers sit the next
-            // step out while warp 0 alone touches what it just repaired.
-        }
-        if (warp == 0) {
-            // first argmax of omega_{T-1}: the last committed omega
-            const double om = wom[fin_b][fin_i][lane];
-            double best = (lane < K) ? om : -CUDART_INF;
-            int bidx = (lane < K) ? lane : 0x7fffffff;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const double ob = __shfl_xor_sync(FULL, best, o);
-                const int oi = __shfl_xor_sync(FULL, bidx, o);
-                if (oi != 0x7fffffff && (bidx == 0x7fffffff || ob > best || (ob == best && oi < bidx))) {
-                    best = ob; bidx = oi;
-                }
-            }
-            if (lane == 0) final_state[blk] = bidx;
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// Viterbi forward sweep, speculation and verification DECOUPLED (K <= 32, few chains).
-//
-// Same idea and same exactness argument as viterbi_spec_kernel, but the runner never waits
-// for a window to be verified: it streams columns into a ring of STR_R slots and only
-// stops when a verifier raises a mismatch.  Roles in a CTA of 16 warps:
+// columns (mean stable stretch 55 columns; 90 % of the pointers are "stay").  So one warp
+// (the runner) advances speculatively with cached pointers — omega_j = (omega_p + log a_pj)
+// + log e_j: exactly-rounded adds and one shared-memory gather per column instead of a K-way
+// arg-max on the dependent chain — while the other warps verify every column it produced with
+// the full exact scan (tournament + hoisting check + literal fallback, as in
+// viterbi_forward_kernel) from the speculative omega of the column before.  Columns before
+// the first mismatch are committed (verified: same adds, same first maximiser as the
+// reference); the mismatching column takes the verifier's result, the pointers are updated
+// and the runner resumes right after it: bit-identical to the sequential sweep by induction
+// over committed columns.  The runner never waits for verification: it streams columns into
+// a ring of STR_R slots and only stops when a verifier raises a mismatch.  (A windowed
+// predecessor — speculate 15 columns, verify, repeat — ran at 172 cycles per column;
+// DESIGN.md section 7.)  Roles in a CTA of 16 warps:
 //   warp 0       runner   omega_t[j] = (max over the candidate pair (lo, hi) of omega_{t-1}[p]
 //                         + log a[p][j]) + log e_t[j]; publishes run_t
 //   warp 15      feeder   stages the log-emission row of every upcoming column in the ring
