@@ -239,6 +239,10 @@ enum itr_phase {
 double itr_phase_ms(itr_ctx *ctx, int phase);
 /* Kernels launched by this context since creation. */
 int64_t itr_launch_count(const itr_ctx *ctx);
+/* Launches of the lock-step FP64 tensor-core sweeps (32 < K <= 96 with many blocks:
+ * optimizer.py:146-238 for eight chains per CTA) since creation — lets a caller or a test
+ * see which path a call took. */
+int64_t itr_lockstep_launch_count(const itr_ctx *ctx);
 int64_t itr_total_columns(const itr_ctx *ctx);
 int64_t itr_num_blocks(const itr_ctx *ctx);
 /* Fills name (NUL-terminated, <= cap bytes), SM count and compute capability. */

@@ -74,6 +74,7 @@ SIGNATURES = {
     "itr_maf_coord_offsets": (_i64p, [ctypes.c_void_p]),
     "itr_phase_ms": (ctypes.c_double, [_c_ctx, ctypes.c_int]),
     "itr_launch_count": (ctypes.c_int64, [_c_ctx]),
+    "itr_lockstep_launch_count": (ctypes.c_int64, [_c_ctx]),
     "itr_total_columns": (ctypes.c_int64, [_c_ctx]),
     "itr_num_blocks": (ctypes.c_int64, [_c_ctx]),
     "itr_device_info": (ctypes.c_int, [_c_ctx, ctypes.c_char_p, ctypes.c_int,

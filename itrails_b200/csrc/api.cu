@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "hmm_kernels.cuh"
+#include "lockstep.h"
 #include "model_build.h"
 #include "csv_writer.h"
 #include "model_plan.h"
@@ -46,7 +47,7 @@ struct itr_ctx {
     int64_t pend_blocks = 0;
     cudaDeviceProp prop{};
     std::string err;
-    int64_t launches = 0;
+    int64_t launches = 0, lockstep_launches = 0;
 
     // blocks
     int64_t n_blocks = 0, n_cols = 0, n_chunks = 0, max_T = 0;
@@ -112,6 +113,8 @@ struct itr_ctx {
 
     // posterior
     double *d_post = nullptr, *d_beta = nullptr;
+    unsigned int *d_ls_ll = nullptr, *d_ls_post = nullptr;     // scratch of the lock-step launches (lockstep.h)
+    size_t cap_ls_ll = 0, cap_ls_post = 0;
     size_t cap_post = 0, cap_beta = 0;
     bool have_post = false;
 
@@ -265,7 +268,7 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
                     ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
                     ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar, ctx->d_Pb, ctx->d_ck_a, ctx->d_ck_b,
-                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile, ctx->d_tile_info};
+                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile, ctx->d_tile_info, ctx->d_ls_ll, ctx->d_ls_post};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -304,6 +307,7 @@ extern "C" double itr_phase_ms(itr_ctx *ctx, int phase) {
 }
 
 extern "C" int64_t itr_launch_count(const itr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t itr_lockstep_launch_count(const itr_ctx *ctx) { return ctx ? ctx->lockstep_launches : 0; }
 extern "C" int64_t itr_total_columns(const itr_ctx *ctx) { return ctx ? ctx->n_cols : 0; }
 extern "C" int64_t itr_num_blocks(const itr_ctx *ctx) { return ctx ? ctx->n_blocks : 0; }
 
@@ -666,6 +670,15 @@ static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
         default: M(32); break;          \
     }
 
+// 32 < K <= 96 with at least two chains per SM: the lock-step sweeps of lockstep.cu
+// (ITR_LOCKSTEP=0|1 forces the choice: experiments, tests)
+static bool use_lockstep(const itr_ctx *ctx, int64_t n_chains) {
+    if (!lockstep_supports(ctx->K)) return false;
+    const char *force = getenv("ITR_LOCKSTEP");
+    if (force) return force[0] == '1';
+    return n_chains >= 2 * (int64_t)ctx->prop.multiProcessorCount;
+}
+
 template <int MODE>
 static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alpha, cudaStream_t st, int slot,
                            int first = 0, int count = -1) {
@@ -676,6 +689,13 @@ static void launch_forward(itr_ctx *ctx, int n_sets, double *d_ll, double *d_alp
         cs.n_blocks = count;
     }
     reset_queue(cs.queue, st);
+    if (MODE == 0 && use_lockstep(ctx, (int64_t)n_sets * cs.n_blocks)) {   // many chains: eight per CTA on the FP64 tensor cores
+        if (ensure(ctx->d_ls_ll, ctx->cap_ls_ll, lockstep_scratch_words((int64_t)n_sets * cs.n_blocks) * 2) != cudaSuccess) return;
+        (void)launch_lockstep_loglik(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, KP, d_ll, ctx->d_ls_ll, ctx->prop.multiProcessorCount, st);
+        ctx->launches += 2;
+        ctx->lockstep_launches += 1;
+        return;
+    }
     if (K > 32 && K <= 96) {        // one CTA of ceil(K/32) warps per chain, columns of a in registers
         const int grid = (int)std::min<int64_t>((int64_t)n_sets * cs.n_blocks, (int64_t)ctx->prop.multiProcessorCount * 8);
         if (K <= 64) sweep_mw_kernel<2, 0, MODE><<<grid, 64, 0, st>>>(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, K, d_ll, d_alpha);
@@ -1164,6 +1184,27 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
     CK(cudaStreamSynchronize(st));
     ctx->ranges_valid = false;
     CK(ensure(ctx->d_post, ctx->cap_post, n));
+    if (use_lockstep(ctx, ctx->n_blocks)) {
+        // many blocks at 32 < K <= 96: four blocks per CTA walked from both ends on the FP64
+        // tensor cores, the two directions meeting in the result matrix (lockstep.cu)
+        CK(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+        phase_begin(ctx, ITR_PH_POST_TOTAL, st);
+        phase_begin(ctx, ITR_PH_POST_COMBINE, st);
+        const ChainSet cs = chain_set(ctx, 1, 3);
+        reset_queue(cs.queue, st);
+        CK(ensure(ctx->d_ls_post, ctx->cap_ls_post, lockstep_scratch_words(ctx->n_blocks)));
+        CK(launch_lockstep_posterior(cs, ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->K, ctx->KP, ctx->d_post, ctx->d_ls_post,
+                                     ctx->prop.multiProcessorCount, st));
+        ctx->launches += 2;
+        ctx->lockstep_launches += 1;
+        phase_end(ctx, ITR_PH_POST_COMBINE, st);
+        phase_end(ctx, ITR_PH_POST_TOTAL, st);
+        ctx->have_post = true;
+        ctx->post_download = false;
+        if (post) CK(cudaMemcpyAsync(post, ctx->d_post, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (!ctx->async) CK(cudaStreamSynchronize(st));
+        return ITR_OK;
+    }
     if (!(ctx->K <= 32 && ctx->use_runs && ctx->runs_valid && !getenv("ITR_NO_RUNS"))) CK(ensure(ctx->d_beta, ctx->cap_beta, n));
     // forward (alpha -> d_post) on the posterior stream, backward (beta -> d_beta) on
     // the second stream, concurrently; then the combine on the posterior stream.

@@ -24,21 +24,12 @@
 
 #include <type_traits>
 
+#include "hmm_common.cuh"
+
 namespace itr {
 
-constexpr int NSYM = 625;
 constexpr int RESCALE = 8;        // columns between power-of-two rescalings
 constexpr int VCHUNK = 256;       // Viterbi traceback chunk (columns)
-constexpr unsigned FULL = 0xffffffffu;
-
-struct ChainSet {
-    const uint16_t *sym;     // all blocks back to back
-    const int64_t *off;      // n_blocks + 1
-    const int32_t *order;    // block ids, longest first
-    int32_t n_blocks;
-    int32_t n_sets;
-    unsigned int *queue;     // work counter (zeroed before launch)
-};
 
 // ---------------------------------------------------------------------------------
 // small helpers

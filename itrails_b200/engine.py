@@ -257,6 +257,11 @@ class Engine:
     def launch_count(self):
         return int(self._lib.itr_launch_count(self._ctx))
 
+    @property
+    def lockstep_launch_count(self):
+        """Launches of the lock-step tensor-core sweeps (32 < K <= 96, many blocks)."""
+        return int(self._lib.itr_lockstep_launch_count(self._ctx))
+
     def device_info(self):
         name = ctypes.create_string_buffer(256)
         sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
