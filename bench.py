@@ -631,7 +631,47 @@ def run_extras(eng, params, n_ab, n_abc, a, b, pi, cores, barrier, args):
                         "column_evaluations_per_s": 1024 * run2.ncol / (build1024 * 1e-3 + sweep_s),
                         "objective_evals_per_s": 1024 / (build1024 * 1e-3 + sweep_s),
                         "finite": bool(np.isfinite(ll1024).all())}
+    extra["config3"] = run_config3(eng, barrier)
     return extra
+
+
+def run_config3(eng, barrier):
+    """Config 3: 100 Mb in 1 000 blocks at (n_int_AB, n_int_ABC) = (5, 5), K = 70 — forward
+    log-likelihood and posterior (kept in HBM: 56 GB) on the lock-step FP64 tensor-core sweeps
+    (csrc/lockstep.cu).  Ten copies of a seeded 10 Mb alignment sampled from the model itself."""
+    from itrails_b200 import synth
+    a, b, pi, _ = eng.build_model(synth.example_model_args(5)[None, :], 5, 5)
+    a, b, pi = a[0], b[0], pi[0]
+    K = a.shape[0]
+    rng = np.random.default_rng(20261018 + 3)
+    lens = synth.block_lengths(100, 10_000_000, rng)
+    V = synth.alignment(a, b, pi, lens, 20261018 + 3)
+    copies = 10
+    lens_all = np.array([len(v) for v in V] * copies, dtype=np.int64)
+    off = np.zeros(len(lens_all) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens_all)
+    eng.load_packed(np.tile(np.concatenate(V).astype(np.uint16), copies), off)
+    n = int(off[-1])
+    l0 = eng.lockstep_launch_count
+    eng.loglik()
+    eng.posterior(fetch=False)
+    ll_ms, post_ms = [], []
+    for _ in range(3):
+        barrier()
+        eng.loglik()
+        ll_ms.append(eng.phase_ms("loglik"))
+        eng.posterior(fetch=False)
+        post_ms.append(eng.phase_ms("post_total"))
+    ll, po = float(np.median(ll_ms)), float(np.median(post_ms))
+    fl_ll, fl_po = n * (2.0 * K * K + 3 * K), n * (2.0 * (2 * K * K + 3 * K) + 3 * K)
+    peak = measured_peaks()[1]
+    return {"workload": "config3", "columns": n, "blocks": int(len(lens_all)), "K": int(K),
+            "loglik_ms": ll, "posterior_ms": po, "posterior_hbm_gb": n * K * 8 / 1e9,
+            "loglik_columns_per_s": n / (ll * 1e-3), "posterior_columns_per_s": n / (po * 1e-3),
+            "loglik_tflops": fl_ll / (ll * 1e-3) / 1e12, "posterior_tflops": fl_po / (po * 1e-3) / 1e12,
+            "posterior_frac_of_fp64_peak": fl_po / (po * 1e-3) / 1e12 / peak,
+            "lockstep_launches": eng.lockstep_launch_count - l0,
+            "note": "device time (CUDA events of the library's phases); flops per column as SURVEY 8(d)"}
 
 
 if __name__ == "__main__":

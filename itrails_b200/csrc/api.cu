@@ -782,16 +782,33 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     // symbols — the same test that enables run compression; else every window mispredicts)
     // (up to ~3 chains per SM the decoupled sweep, one CTA per chain pulled longest-first from
     // the queue, beats one warp per chain: 133 against ~360 cycles per column)
-    const bool want_stream = vmode ? !strcmp(vmode, "stream") : (ctx->use_runs && ctx->n_blocks <= (int64_t)3 * sms);
+    // Chains per SM decide the CTA shape: one 16-warp CTA per SM up to 1.5 chains per SM (the
+    // fastest column: 133 cycles), two 8-warp CTAs up to 3, three 5-warp CTAs beyond (hundreds of
+    // chains: a GPU's share of a chromosome split over several GPUs); with thousands of chains
+    // the check-first sweep below wins (ITR_VSTREAM_MAX: chains per SM up to which this one is used).
+    static const char *smax = getenv("ITR_VSTREAM_MAX");      // experiments
+    const double per_sm = (double)ctx->n_blocks / sms;
+    const bool want_stream = vmode ? !strncmp(vmode, "stream", 6) : (ctx->use_runs && per_sm <= (smax ? atof(smax) : 7.0));
     if (K <= 32 && want_stream && ctx->max_T < 0x7fffffff) {
-        // decoupled speculate-and-verify sweep: runner, feeder and 14 verifiers per chain
-        const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms);
-        const size_t shs = (size_t)(NSYM * 32 + 2 * STR_R * 32) * sizeof(double) + (size_t)STR_R * 32;
-#define VSTR(KT)                                                                                               \
-    do {                                                                                                       \
-        cudaFuncSetAttribute(viterbi_stream_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shs); \
-        viterbi_stream_kernel<KT><<<grid, 32 * STR_NW, shs, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K,    \
-                                                                  ctx->d_bp, ctx->d_final);                    \
+        int nw = per_sm <= 2.5 ? 16 : 8;
+        if (vmode && !strcmp(vmode, "stream16")) nw = 16;
+        if (vmode && !strcmp(vmode, "stream8")) nw = 8;
+        if (vmode && !strcmp(vmode, "stream5")) nw = 5;
+        static const char *sper = getenv("ITR_VSTREAM_PER");     // experiments: CTAs per SM
+        const int per = sper ? atoi(sper) : nw == 16 ? 1 : nw == 8 ? 2 : 3;
+        const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms * per);
+#define VSTR2(KT, NWP)                                                                                            \
+    do {                                                                                                         \
+        const size_t shs = StreamCfg<NWP>::SMEM;                                                                  \
+        cudaFuncSetAttribute(viterbi_stream_kernel<KT, NWP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shs); \
+        viterbi_stream_kernel<KT, NWP><<<grid, 32 * NWP, shs, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K,      \
+                                                                    ctx->d_bp, ctx->d_final);                    \
+    } while (0)
+#define VSTR(KT)                      \
+    do {                              \
+        if (nw == 16) VSTR2(KT, 16);  \
+        else if (nw == 8) VSTR2(KT, 8); \
+        else VSTR2(KT, 5);            \
     } while (0)
         switch ((K + 3) / 4) {
             case 1: VSTR(4); break;
@@ -804,6 +821,7 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
             default: VSTR(32); break;
         }
 #undef VSTR
+#undef VSTR2
         return;
     }
     if (K <= 32 && (vmode ? !strcmp(vmode, "4warp") : ctx->n_blocks <= (int64_t)4 * sms) && !getenv("ITR_VITERBI_1WARP")) {

@@ -908,7 +908,14 @@ __device__ __forceinline__ void quad_rescale(double (&x)[NQ]) {
 #define ITR_MMA_UNROLL 4
 #endif
 constexpr int MMA_UNROLL = ITR_MMA_UNROLL;
-constexpr int MMA_WARPS = 8;                       // warps per CTA, four tiles each
+#ifndef ITR_MMA_WARPS
+#define ITR_MMA_WARPS 4
+#endif
+// warps per CTA, four tiles each.  Four warps (111 KB of shared memory, 28 k registers): two
+// CTAs fill an SM when the kernel is alone, and ONE still fits next to a Viterbi CTA when the
+// recursions of a step overlap (an 8-warp CTA needs the whole SM and waits for the Viterbi
+// sweep to end).
+constexpr int MMA_WARPS = ITR_MMA_WARPS;
 
 template <int KT>
 __global__ void __launch_bounds__(32 * MMA_WARPS, 1)
@@ -1954,7 +1961,7 @@ __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, do
 // ISOLATE: warps 4, 8, 12 stay idle so that the runner has its scheduler (and its FP64
 // pipe) to itself; 11 verifiers on the other three schedulers still verify ~2x faster
 // than the runner produces.
-constexpr int STR_R = 64, STR_NW = 16, STR_NV = ITR_STR_ISOLATE ? 11 : 14;
+constexpr int STR_R = 64;
 #ifndef ITR_STR_G
 #define ITR_STR_G 8
 #endif
@@ -1964,32 +1971,51 @@ constexpr int STR_NONE = 0x7fffffff;
 #define ITR_STR_SLEEP 200
 #endif
 
-template <int KT>
-__global__ void __launch_bounds__(32 * STR_NW)
+// NWARPS = 16: one chain per SM (up to ~1.5 chains per SM in the queue): runner, feeder, 11
+//              verifiers, three idle warps; the log-emission table (160 KB) in shared memory.
+// NWARPS = 8 / 5: two / three chains per SM for hundreds of chains (a GPU's share of a
+//              chromosome split over 4-8 GPUs): runner, feeder, 6 / 3 verifiers; the feeder reads
+//              the emission rows through L1 instead (it is off the chain), so a CTA needs only
+//              its rings (43 KB) and several fit an SM.  The runner shares its scheduler.
+template <int NWARPS>
+struct StreamCfg {
+    static constexpr bool ISOLATE = NWARPS == 16 && ITR_STR_ISOLATE;
+    static constexpr bool TABLE = NWARPS == 16;                       // log-emission table in shared memory
+    static constexpr int NV = ISOLATE ? 11 : NWARPS - 2;
+    static constexpr int SLOTS = NWARPS <= 8 ? 8 : 16;                // verifier slots (power of two >= NV)
+    static constexpr size_t SMEM = (size_t)((TABLE ? NSYM * 32 : 0) + 2 * STR_R * 32) * sizeof(double) + (size_t)STR_R * 32;
+};
+
+template <int KT, int NWARPS>
+__global__ void __launch_bounds__(32 * NWARPS)
 viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                       const double *__restrict__ OM0, int K,
                       uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
+    using Cfg = StreamCfg<NWARPS>;
+    constexpr int STR_NW = NWARPS, STR_NV = Cfg::NV, STR_SL = Cfg::SLOTS;
     constexpr int KP = 32, R = STR_R, NV = STR_NV;
     __shared__ double las[KP][KP];                      // log a, for the runner's pointer lookups
-    __shared__ __align__(16) double vrom[STR_NW][KP];   // verified omega of a mismatching column, per verifier
-    __shared__ int varg[STR_NW][KP];                    // its verified first arg-maxima
-    __shared__ volatile int vfail[STR_NW];              // the column it belongs to (STR_NONE: none)
-    __shared__ volatile int ver_next[STR_NW];           // next column each verifier will look at
+    __shared__ __align__(16) double vrom[STR_SL][KP];   // verified omega of a mismatching column, per verifier
+    __shared__ int varg[STR_SL][KP];                    // its verified first arg-maxima
+    __shared__ volatile int vfail[STR_SL];              // the column it belongs to (STR_NONE: none)
+    __shared__ volatile int ver_next[STR_SL];           // next column each verifier will look at
     __shared__ volatile int run_t, feed_t, fail_t;      // last column produced / staged (exclusive) / first bad column
     __shared__ int chain_s;
     extern __shared__ __align__(16) double dyn[];
-    double *les = dyn;                                                   // [NSYM][KP] log-emission table
-    double (*ring_om)[KP] = reinterpret_cast<double (*)[KP]>(dyn + NSYM * KP);          // omega after column t, slot t % R
-    double (*ring_ew)[KP] = reinterpret_cast<double (*)[KP]>(dyn + NSYM * KP + R * KP); // log e row of column t
-    uint8_t (*ring_ptr)[KP] = reinterpret_cast<uint8_t (*)[KP]>(dyn + NSYM * KP + 2 * R * KP);  // the runner's choice
+    constexpr int TAB = Cfg::TABLE ? NSYM * KP : 0;
+    double *les = dyn;                                                   // [NSYM][KP] log-emission table (NWARPS = 16)
+    double (*ring_om)[KP] = reinterpret_cast<double (*)[KP]>(dyn + TAB);          // omega after column t, slot t % R
+    double (*ring_ew)[KP] = reinterpret_cast<double (*)[KP]>(dyn + TAB + R * KP); // log e row of column t
+    uint8_t (*ring_ptr)[KP] = reinterpret_cast<uint8_t (*)[KP]>(dyn + TAB + 2 * R * KP);  // the runner's choice
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_chains = cs.n_blocks;
     const int K4 = (K + 3) & ~3;
-    for (int e = threadIdx.x; e < NSYM * KP; e += blockDim.x) les[e] = __ldg(LEt + e);
+    if (Cfg::TABLE)
+        for (int e = threadIdx.x; e < NSYM * KP; e += blockDim.x) les[e] = __ldg(LEt + e);
     Cols<KT, 1, true> lacol;                            // column `lane` of log a (verifiers)
     // verifier index of this warp (-1: runner, feeder or idle)
     const int vi = (warp == 0 || warp == STR_NW - 1) ? -1
-                   : ITR_STR_ISOLATE ? ((warp & 3) ? warp - 1 - (warp >> 2) : -1) : warp - 1;
+                   : Cfg::ISOLATE ? ((warp & 3) ? warp - 1 - (warp >> 2) : -1) : warp - 1;
     if (vi >= 0) lacol.load(LA, KP, lane);
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) las[e / KP][e % KP] = __ldg(LA + e);
     __syncthreads();
@@ -2096,7 +2122,7 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                     const int mysym = (int)__ldg(symp + t_feed + lane);     // (64 columns of slack behind the last block)
                     for (int i = 0; i < n; ++i) {
                         const int sy = __shfl_sync(FULL, mysym, i);
-                        ring_ew[(t_feed + i) & (R - 1)][lane] = les[sy * KP + lane];
+                        ring_ew[(t_feed + i) & (R - 1)][lane] = Cfg::TABLE ? les[sy * KP + lane] : __ldg(LEt + sy * KP + lane);
                     }
                     t_feed += n;
                     __threadfence_block();
@@ -2166,7 +2192,7 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
             int np2 = 0, chosen = 0;
             double fix_om = 0.0;
             if (warp == 0 && f < T) {
-                const int vf = vfail[lane & (STR_NW - 1)];
+                const int vf = vfail[lane & (STR_SL - 1)];
                 const unsigned who = __ballot_sync(FULL, lane < NV && vf == f);
                 const int v = who ? __ffs(who) - 1 : 0;
 #ifdef ITR_STR_DEBUG
