@@ -782,10 +782,11 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     // symbols — the same test that enables run compression; else every window mispredicts)
     // (up to ~3 chains per SM the decoupled sweep, one CTA per chain pulled longest-first from
     // the queue, beats one warp per chain: 133 against ~360 cycles per column)
-    // Chains per SM decide the CTA shape: one 16-warp CTA per SM up to 1.5 chains per SM (the
-    // fastest column: 133 cycles), two 8-warp CTAs up to 3, three 5-warp CTAs beyond (hundreds of
-    // chains: a GPU's share of a chromosome split over several GPUs); with thousands of chains
-    // the check-first sweep below wins (ITR_VSTREAM_MAX: chains per SM up to which this one is used).
+    // Chains per SM decide the CTA shape: one 16-warp CTA per SM up to 2.5 chains per SM (the
+    // fastest column: 133 cycles; chains wait in the queue), two 8-warp CTAs per SM up to 7
+    // (hundreds of chains: a GPU's share of a chromosome split over several GPUs); with
+    // thousands of chains the check-first sweep below wins (measured: tools/time_vit_modes.py;
+    // ITR_VSTREAM_MAX: chains per SM up to which this sweep is used).
     static const char *smax = getenv("ITR_VSTREAM_MAX");      // experiments
     const double per_sm = (double)ctx->n_blocks / sms;
     const bool want_stream = vmode ? !strncmp(vmode, "stream", 6) : (ctx->use_runs && per_sm <= (smax ? atof(smax) : 7.0));
@@ -793,9 +794,8 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
         int nw = per_sm <= 2.5 ? 16 : 8;
         if (vmode && !strcmp(vmode, "stream16")) nw = 16;
         if (vmode && !strcmp(vmode, "stream8")) nw = 8;
-        if (vmode && !strcmp(vmode, "stream5")) nw = 5;
         static const char *sper = getenv("ITR_VSTREAM_PER");     // experiments: CTAs per SM
-        const int per = sper ? atoi(sper) : nw == 16 ? 1 : nw == 8 ? 2 : 3;
+        const int per = sper ? atoi(sper) : nw == 16 ? 1 : 2;
         const int grid = (int)std::min<int64_t>(ctx->n_blocks, (int64_t)sms * per);
 #define VSTR2(KT, NWP)                                                                                            \
     do {                                                                                                         \
@@ -807,8 +807,7 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
 #define VSTR(KT)                      \
     do {                              \
         if (nw == 16) VSTR2(KT, 16);  \
-        else if (nw == 8) VSTR2(KT, 8); \
-        else VSTR2(KT, 5);            \
+        else VSTR2(KT, 8);            \
     } while (0)
         switch ((K + 3) / 4) {
             case 1: VSTR(4); break;

@@ -1973,10 +1973,10 @@ constexpr int STR_NONE = 0x7fffffff;
 
 // NWARPS = 16: one chain per SM (up to ~1.5 chains per SM in the queue): runner, feeder, 11
 //              verifiers, three idle warps; the log-emission table (160 KB) in shared memory.
-// NWARPS = 8 / 5: two / three chains per SM for hundreds of chains (a GPU's share of a
-//              chromosome split over 4-8 GPUs): runner, feeder, 6 / 3 verifiers; the feeder reads
-//              the emission rows through L1 instead (it is off the chain), so a CTA needs only
-//              its rings (43 KB) and several fit an SM.  The runner shares its scheduler.
+// NWARPS = 8:  two chains per SM for hundreds of chains (a GPU's share of a chromosome split
+//              over 4-8 GPUs): runner, feeder, 6 verifiers; the feeder reads the emission rows
+//              through L1 instead (it is off the chain), so a CTA needs only its rings (46 KB)
+//              and two fit an SM.  The runner shares its scheduler with a verifier.
 template <int NWARPS>
 struct StreamCfg {
     static constexpr bool ISOLATE = NWARPS == 16 && ITR_STR_ISOLATE;
