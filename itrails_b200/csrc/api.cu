@@ -835,7 +835,7 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     }
     const Geometry g = geometry(ctx, ctx->n_blocks, 16);
     const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
-    if (K <= 32 && (vmode ? !strcmp(vmode, "check") : ctx->use_runs)) {
+    if (K <= 32 && (vmode ? !strncmp(vmode, "check", 5) : ctx->use_runs)) {
         // many chains, stable backpointers: check the cached pointer, exact scan only on a miss.
         // One chain per warp, CTAs of four warps; at most `wps` warps per SM: more resident
         // chains than that only stretch every chain's column latency (they share one FP64
@@ -846,9 +846,20 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
         g.warps = 4;
         g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n_blocks + 3) / 4, (int64_t)sms * (wps / 4)));
         const size_t sh = (size_t)g.warps * 2 * KP * sizeof(double);
+        if (vmode && !strcmp(vmode, "check64")) {        // the all-FP64 check (experiments, tests)
 #define VCHK(KT) viterbi_check_kernel<KT><<<g.grid, g.warps * 32, sh, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
-        ITR_SWITCH_KT(K, VCHK)
+            ITR_SWITCH_KT(K, VCHK)
 #undef VCHK
+            return;
+        }
+        // default: the same check behind an FP32 screen (16 warps per SM)
+        static const char *w32 = getenv("ITR_VCHK32_WPS");          // experiments
+        const int wps32 = w32 ? std::max(4, atoi(w32)) : 16;
+        g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n_blocks + 3) / 4, (int64_t)sms * (wps32 / 4)));
+        const size_t sh32 = (size_t)g.warps * 3 * KP * sizeof(double);
+#define VCHK32(KT) viterbi_check32_kernel<KT><<<g.grid, g.warps * 32, sh32, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
+        ITR_SWITCH_KT(K, VCHK32)
+#undef VCHK32
         return;
     }
 #define VIT_REG(KT)                                                        \

@@ -1735,6 +1735,137 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
 }
 
 // ---------------------------------------------------------------------------------
+// Check-first sweep with an FP32 SCREEN (K <= 32, many chains).
+//
+// viterbi_check_kernel spends two FP64 operations per predecessor and column (form the sum,
+// test it against s_p) only to learn, 98 % of the time, that the cached pointer still wins
+// by several nats.  Here that question is first asked in single precision, on DIFFERENCES:
+// every lane publishes d_i = float(omega_i - ref) next to omega_i (ref: omega_0 of the
+// previous column, the same double in every lane, so the difference is taken in FP64 and
+// only then rounded), and lane j compares s'_p = d_p + float(log a_pj) with the largest of
+// the other s'_i = d_i + float(log a_ij) — FADD / FMNMX on the FP32 pipe, half as many
+// shared-memory wavefronts, the column of log a in 28 registers instead of 56.  The errors
+// are bounded: each s' is within 3 * 2^-24 * max(|d|, |log a|, |s'|) of the exact real sum,
+// the FP64 sums s_i of the reference within 2^-53 relative; for |s'_p| < 4096 that is
+// < 8e-4 per side.  So  s'_p - max_i s'_i > 2^-8  PROVES that s_p is the strict, unique
+// maximum of the reference's FP64 sums — the cached pointer is np.argmax's answer — and the
+// column's omega is then formed exactly as the reference does, in FP64, from that pointer:
+// (omega_p + log a_pj) + log e_j, with the usual hoisting test.  Anything else — a margin
+// inside the band (ties and near-ties), a lost pointer, magnitudes beyond the bound, NaN —
+// goes to the exact FP64 column (viterbi_full_column), as in viterbi_check_kernel.
+// Bit-identical paths by construction; FP64 work per column falls from ~56 to ~6 operations.
+// ---------------------------------------------------------------------------------
+#ifndef ITR_VCHK32_MINB
+#define ITR_VCHK32_MINB 3
+#endif
+template <int KT>
+__global__ void __launch_bounds__(128, ITR_VCHK32_MINB)
+viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
+                       const double *__restrict__ OM0, int K,
+                       uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
+    constexpr int KP = 32;
+    constexpr float BAND = 0.00390625f, BOUND = 4096.f;       // 2^-8, see above
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xs = smem + (size_t)warp * 3 * KP;                 // omega, double buffered (2 KP doubles)
+    float *fs = reinterpret_cast<float *>(xs + 2 * KP);        // the differences, double buffered (2 KP floats)
+    const int n_chains = cs.n_blocks;
+    const int K4 = (K + 3) & ~3;
+    const double *etl = LEt + lane;
+    // column `lane` of log a in single precision, the cached pointer's entry replaced by -inf
+    float laf[KT];
+    auto load_column_without = [&](int p) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) laf[i] = (i == p) ? -CUDART_INF_F : (float)__ldg(LA + (size_t)i * KP + lane);
+    };
+
+    for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
+        const int blk = cs.order[c];
+        const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
+        const SymTile st{cs.sym + beg, T};
+        uint8_t *bpt = bp + (size_t)beg * KP + lane + KP;        // row of column t = 1
+
+        int p = lane;                                            // cached pointer: "stay"
+        double la_p = __ldg(LA + (size_t)lane * KP + lane);
+        float laf_p = (float)la_p;
+        load_column_without(p);
+        unsigned vcur = st.load(0, lane), vnxt = st.load(32, lane);
+        double om = __ldg(OM0 + (size_t)blk * KP + lane);
+        double ref = __shfl_sync(FULL, om, 0);
+        double e1 = __ldg(etl + __shfl_sync(FULL, vcur, 1) * KP), e2 = __ldg(etl + __shfl_sync(FULL, vcur, 2) * KP);
+        unsigned vpre = tile_symbol(vcur, vnxt, 3);              // symbol of the column two ahead
+        int buf = 0;
+        auto column = [&](int s32) {
+            double *xb = xs + buf * KP;
+            float *fb = fs + buf * KP;
+            xb[lane] = om;
+            fb[lane] = (float)__dsub_rn(om, ref);
+            __syncwarp();
+            buf ^= 1;
+            const double e3 = __ldg(etl + vpre * KP);
+            vpre = tile_symbol(vcur, vnxt, s32 + 4);
+            // exact part: the reference's two adds for the cached pointer
+            const double s_p = __dadd_rn(xb[p], la_p);
+            double M = __dadd_rn(s_p, e1);
+            // screen: is any other predecessor within the band of s_p?
+            const float fp = fb[p] + laf_p;
+            const float4 *f4 = reinterpret_cast<const float4 *>(fb);
+            float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+#pragma unroll
+            for (int i = 0; i < KT; i += 4) {
+                const float4 q = f4[i / 4];
+                m0 = fmaxf(m0, q.x + laf[i]);
+                m1 = fmaxf(m1, q.y + laf[i + 1]);
+                m2 = fmaxf(m2, q.z + laf[i + 2]);
+                m3 = fmaxf(m3, q.w + laf[i + 3]);
+            }
+            const float other = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            const double ref_next = xb[0];
+            const bool proven = (fp - other > BAND) & (fabsf(fp) < BOUND);
+            const bool bad = (lane < K) & (!proven | viterbi_hoist_unsafe(s_p, e1, M));
+            if (__builtin_expect(__any_sync(FULL, bad), 0)) {
+                const ScanResult r = viterbi_full_column<KT>(xb, LA + lane, K, K4, e1);
+                M = r.best;
+                if (r.arg != p) {
+                    p = r.arg;
+                    la_p = __ldg(LA + (size_t)p * KP + lane);
+                    laf_p = (float)la_p;
+                    load_column_without(p);
+                }
+            }
+            om = M;
+            ref = ref_next;
+            *bpt = (uint8_t)p;
+            bpt += KP;
+            e1 = e2;
+            e2 = e3;
+        };
+        int64_t t0 = 0;
+        for (; t0 + 32 < T; t0 += 32) {
+#pragma unroll 2
+            for (int s32 = 0; s32 < 32; ++s32) column(s32);
+            vcur = vnxt;
+            vnxt = st.load(t0 + 64, lane);
+        }
+#pragma unroll 1
+        for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32);
+        // first argmax of omega_{T-1}
+        double best = (lane < K) ? om : -CUDART_INF;
+        int bidx = (lane < K) ? lane : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, bidx, o);
+            if (oi != 0x7fffffff && (bidx == 0x7fffffff || ob > best || (ob == best && oi < bidx))) {
+                best = ob; bidx = oi;
+            }
+        }
+        if (lane == 0) final_state[blk] = bidx;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Viterbi forward sweep, four warps per chain (K <= 32).  With few chains (config 2:
 // 100 blocks on 148 SMs) the sweep is bound by the per-column latency of one warp's
 // ~200-instruction argmax.  Here a CTA of four warps (one per SM sub-partition) walks

@@ -195,7 +195,7 @@ def test_reference_style_wrappers(engine):
         assert np.abs(post[i] - g[f"post_{i}"]).max() <= POST_ATOL
 
 
-@pytest.mark.parametrize("variant", ["stream", "stream8", "4warp", "1warp", "check"])
+@pytest.mark.parametrize("variant", ["stream", "stream8", "4warp", "1warp", "check", "check64"])
 def test_viterbi_kernel_variants_agree(engine, variant, monkeypatch):
     """The speculate-and-verify sweep (few chains; 16- and 8-warp CTAs), the four-warps-per-chain sweep and the
     one-warp-per-chain sweep (many chains) are all bit-exact against the oracle, on

@@ -22,7 +22,7 @@ for world in (8, 4, 2, 1):
     eng.set_model(a, b, pi)
     tabs = viterbi_tables(a, b, pi, V)
     ref = None
-    for mode in (None, "stream16", "stream8", "stream5", "4warp", "check"):
+    for mode in (None, "stream16", "stream8", "4warp", "check", "check64"):
         if mode is None: os.environ.pop("ITR_VITERBI", None)
         else: os.environ["ITR_VITERBI"] = mode
         for _ in range(2): path = eng.viterbi(*tabs)
