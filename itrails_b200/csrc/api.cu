@@ -852,9 +852,9 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
 #undef VCHK
             return;
         }
-        // default: the same check behind an FP32 screen (16 warps per SM)
+        // default: the same check behind an FP32 screen
         static const char *w32 = getenv("ITR_VCHK32_WPS");          // experiments
-        const int wps32 = w32 ? std::max(4, atoi(w32)) : 16;
+        const int wps32 = w32 ? std::max(4, atoi(w32)) : 12;
         g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n_blocks + 3) / 4, (int64_t)sms * (wps32 / 4)));
         const size_t sh32 = (size_t)g.warps * 3 * KP * sizeof(double);
 #define VCHK32(KT) viterbi_check32_kernel<KT><<<g.grid, g.warps * 32, sh32, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)

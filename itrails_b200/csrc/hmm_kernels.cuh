@@ -1743,18 +1743,52 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
 // every lane publishes d_i = float(omega_i - ref) next to omega_i (ref: omega_0 of the
 // previous column, the same double in every lane, so the difference is taken in FP64 and
 // only then rounded), and lane j compares s'_p = d_p + float(log a_pj) with the largest of
-// the other s'_i = d_i + float(log a_ij) — FADD / FMNMX on the FP32 pipe, half as many
-// shared-memory wavefronts, the column of log a in 28 registers instead of 56.  The errors
-// are bounded: each s' is within 3 * 2^-24 * max(|d|, |log a|, |s'|) of the exact real sum,
-// the FP64 sums s_i of the reference within 2^-53 relative; for |s'_p| < 4096 that is
-// < 8e-4 per side.  So  s'_p - max_i s'_i > 2^-8  PROVES that s_p is the strict, unique
-// maximum of the reference's FP64 sums — the cached pointer is np.argmax's answer — and the
-// column's omega is then formed exactly as the reference does, in FP64, from that pointer:
-// (omega_p + log a_pj) + log e_j, with the usual hoisting test.  Anything else — a margin
-// inside the band (ties and near-ties), a lost pointer, magnitudes beyond the bound, NaN —
-// goes to the exact FP64 column (viterbi_full_column), as in viterbi_check_kernel.
-// Bit-identical paths by construction; FP64 work per column falls from ~56 to ~6 operations.
+// the other s'_i = d_i + float(log a_ij) — FADD2 / FMNMX3 on the FP32 pipe, half as many
+// shared-memory wavefronts, the column of log a in 28 registers instead of 56.
+// Error bound.  The screen is only trusted in a column where every finite d_i and every
+// finite log a_ij is below 64 in magnitude (else: exact path).  Then each s'_i is within
+// 2^-24 (|d_i| + |log a_ij| + |s'_i|) < 2^-24 * 256 = 1.6e-5 of the real number
+// (omega_i - ref) + log a_ij, and the reference's FP64 sum fl(omega_i + log a_ij) within
+// 2^-53 |s_i| (< 1e-10) of that number + ref.  So  s'_p - max_i s'_i > 2^-14 = 6.1e-5  PROVES
+// that s_p is the strict, unique maximum of the reference's sums — the cached pointer is
+// np.argmax's answer — and the column's omega is then formed exactly as the reference does,
+// in FP64, from that pointer: (omega_p + log a_pj) + log e_j, with the usual hoisting test.
+// A margin inside the band (ties and near-ties) is decided by the FP64 check of
+// viterbi_check_kernel, out of line; a lost pointer, an unsafe hoist, magnitudes beyond the
+// bound or NaN by the exact FP64 column (viterbi_full_column).  Bit-identical paths by
+// construction; FP64 work per column falls from ~56 to ~7 operations.
 // ---------------------------------------------------------------------------------
+// FP64 check of the cached pointer for the calling warp (cold path of viterbi_check32_kernel):
+// true if some lane's s_p is NOT the strict unique maximum of its K sums.
+template <int KT>
+__device__ __noinline__ bool viterbi_pointer_beaten(const double *xb, const double *lac, int p, double s_p) {
+    constexpr int KP = 32;
+    const double2 *x2 = reinterpret_cast<const double2 *>(xb);
+    const long long pb = __double_as_longlong(s_p);
+    const double t = __longlong_as_double(pb - ((pb >> 63) | 1));         // pred(s_p): s_i >= s_p <=> t - s_i < 0
+    unsigned sg = 0u;
+#pragma unroll
+    for (int i = 0; i < KT; i += 2) {
+        const double2 pq = x2[i / 2];
+        const double l0 = (i == p) ? -CUDART_INF : __ldg(lac + (size_t)i * KP);
+        const double l1 = (i + 1 == p) ? -CUDART_INF : __ldg(lac + (size_t)(i + 1) * KP);
+        sg |= (unsigned)__double2hiint(__dsub_rn(t, __dadd_rn(pq.x, l0))) | (unsigned)__double2hiint(__dsub_rn(t, __dadd_rn(pq.y, l1)));
+    }
+    return (int)sg < 0;
+}
+
+// sm_100: two FP32 adds in one instruction (FADD2) and a three-input maximum (FMNMX3)
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float max3_f32(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 #ifndef ITR_VCHK32_MINB
 #define ITR_VCHK32_MINB 3
 #endif
@@ -1764,7 +1798,7 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
                        const double *__restrict__ OM0, int K,
                        uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
     constexpr int KP = 32;
-    constexpr float BAND = 0.00390625f, BOUND = 4096.f;       // 2^-8, see above
+    constexpr float BAND = 6.103515625e-5f, BOUND = 64.f;      // 2^-14 and the magnitude bound, see above
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *xs = smem + (size_t)warp * 3 * KP;                 // omega, double buffered (2 KP doubles)
@@ -1772,12 +1806,26 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
     const int n_chains = cs.n_blocks;
     const int K4 = (K + 3) & ~3;
     const double *etl = LEt + lane;
-    // column `lane` of log a in single precision, the cached pointer's entry replaced by -inf
-    float laf[KT];
+    // column `lane` of log a in single precision, two entries per 64-bit register (the scan
+    // uses the packed FADD2 and the three-input FMNMX3 of sm_100: 28 instructions for 28
+    // predecessors), the cached pointer's entry replaced by -inf
+    unsigned long long laf2[KT / 2];
     auto load_column_without = [&](int p) {
 #pragma unroll
-        for (int i = 0; i < KT; ++i) laf[i] = (i == p) ? -CUDART_INF_F : (float)__ldg(LA + (size_t)i * KP + lane);
+        for (int i = 0; i < KT; i += 2) {
+            const float l0 = (i == p) ? -CUDART_INF_F : (float)__ldg(LA + (size_t)i * KP + lane);
+            const float l1 = (i + 1 == p) ? -CUDART_INF_F : (float)__ldg(LA + (size_t)(i + 1) * KP + lane);
+            laf2[i / 2] = (unsigned long long)__float_as_uint(l0) | ((unsigned long long)__float_as_uint(l1) << 32);
+        }
     };
+    // is every finite entry of this lane's column of log a inside the bound?  (-inf: that
+    // predecessor can never be near the maximum)
+    bool la_ok = true;
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+        const float l = (float)__ldg(LA + (size_t)i * KP + lane);
+        la_ok &= (l == -CUDART_INF_F) | (fabsf(l) < BOUND);
+    }
 
     for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
         const int blk = cs.order[c];
@@ -1798,8 +1846,9 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
         auto column = [&](int s32) {
             double *xb = xs + buf * KP;
             float *fb = fs + buf * KP;
+            const float d = (float)__dsub_rn(om, ref);
             xb[lane] = om;
-            fb[lane] = (float)__dsub_rn(om, ref);
+            fb[lane] = d;
             __syncwarp();
             buf ^= 1;
             const double e3 = __ldg(etl + vpre * KP);
@@ -1809,28 +1858,35 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             double M = __dadd_rn(s_p, e1);
             // screen: is any other predecessor within the band of s_p?
             const float fp = fb[p] + laf_p;
-            const float4 *f4 = reinterpret_cast<const float4 *>(fb);
-            float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+            const ulonglong2 *f4 = reinterpret_cast<const ulonglong2 *>(fb);
+            float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
 #pragma unroll
             for (int i = 0; i < KT; i += 4) {
-                const float4 q = f4[i / 4];
-                m0 = fmaxf(m0, q.x + laf[i]);
-                m1 = fmaxf(m1, q.y + laf[i + 1]);
-                m2 = fmaxf(m2, q.z + laf[i + 2]);
-                m3 = fmaxf(m3, q.w + laf[i + 3]);
+                const ulonglong2 q = f4[i / 4];
+                const unsigned long long r01 = add_f32x2(q.x, laf2[i / 2]), r23 = add_f32x2(q.y, laf2[i / 2 + 1]);
+                m0 = max3_f32(m0, __uint_as_float((unsigned)r01), __uint_as_float((unsigned)(r01 >> 32)));
+                m1 = max3_f32(m1, __uint_as_float((unsigned)r23), __uint_as_float((unsigned)(r23 >> 32)));
             }
-            const float other = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            const float other = fmaxf(m0, m1);
             const double ref_next = xb[0];
-            const bool proven = (fp - other > BAND) & (fabsf(fp) < BOUND);
-            const bool bad = (lane < K) & (!proven | viterbi_hoist_unsafe(s_p, e1, M));
-            if (__builtin_expect(__any_sync(FULL, bad), 0)) {
-                const ScanResult r = viterbi_full_column<KT>(xb, LA + lane, K, K4, e1);
-                M = r.best;
-                if (r.arg != p) {
-                    p = r.arg;
-                    la_p = __ldg(LA + (size_t)p * KP + lane);
-                    laf_p = (float)la_p;
-                    load_column_without(p);
+            // the bound on |d| is a property of the column: every live lane votes on its own d
+            const bool d_ok = (lane >= K) | (d == -CUDART_INF_F) | (fabsf(d) < BOUND);
+            const bool trusted = __all_sync(FULL, d_ok) & la_ok;
+            const bool proven = trusted & (fp - other > BAND);
+            const bool unsafe = viterbi_hoist_unsafe(s_p, e1, M);
+            if (__builtin_expect(__any_sync(FULL, (lane < K) & (!proven | unsafe)), 0)) {
+                // band, bound or hoist: the FP64 check decides whether the pointers stand
+                bool redo = __any_sync(FULL, (lane < K) & unsafe);
+                if (!redo) redo = __any_sync(FULL, (lane < K) & viterbi_pointer_beaten<KT>(xb, LA + lane, p, s_p));
+                if (redo) {
+                    const ScanResult r = viterbi_full_column<KT>(xb, LA + lane, K, K4, e1);
+                    M = r.best;
+                    if (r.arg != p) {
+                        p = r.arg;
+                        la_p = __ldg(LA + (size_t)p * KP + lane);
+                        laf_p = (float)la_p;
+                        load_column_without(p);
+                    }
                 }
             }
             om = M;
