@@ -782,8 +782,8 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     // symbols — the same test that enables run compression; else every window mispredicts)
     // (up to ~3 chains per SM the decoupled sweep, one CTA per chain pulled longest-first from
     // the queue, beats one warp per chain: 133 against ~360 cycles per column)
-    // Chains per SM decide the CTA shape: one 16-warp CTA per SM up to 2.5 chains per SM (the
-    // fastest column: 133 cycles; chains wait in the queue), two 8-warp CTAs per SM up to 7
+    // Chains per SM decide the CTA shape: one 16-warp CTA per SM up to one chain per SM (the
+    // fastest column: 133 cycles), two 8-warp CTAs per SM (screened verifiers) up to 7
     // (hundreds of chains: a GPU's share of a chromosome split over several GPUs); with
     // thousands of chains the check-first sweep below wins (measured: tools/time_vit_modes.py;
     // ITR_VSTREAM_MAX: chains per SM up to which this sweep is used).
@@ -791,7 +791,7 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
     const double per_sm = (double)ctx->n_blocks / sms;
     const bool want_stream = vmode ? !strncmp(vmode, "stream", 6) : (ctx->use_runs && per_sm <= (smax ? atof(smax) : 7.0));
     if (K <= 32 && want_stream && ctx->max_T < 0x7fffffff) {
-        int nw = per_sm <= 2.5 ? 16 : 8;
+        int nw = per_sm <= 1.0 ? 16 : 8;
         if (vmode && !strcmp(vmode, "stream16")) nw = 16;
         if (vmode && !strcmp(vmode, "stream8")) nw = 8;
         static const char *sper = getenv("ITR_VSTREAM_PER");     // experiments: CTAs per SM
