@@ -2181,8 +2181,11 @@ struct StreamCfg {
     static constexpr size_t SMEM = (size_t)((TABLE ? NSYM * 32 : 0) + 2 * STR_R * 32) * sizeof(double) + (size_t)STR_R * 32;
 };
 
+#ifndef ITR_STR8_MINB
+#define ITR_STR8_MINB 1
+#endif
 template <int KT, int NWARPS>
-__global__ void __launch_bounds__(32 * NWARPS)
+__global__ void __launch_bounds__(32 * NWARPS, NWARPS == 8 ? ITR_STR8_MINB : 1)
 viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                       const double *__restrict__ OM0, int K,
                       uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
