@@ -1588,6 +1588,10 @@ viterbi_forward_kernel(ChainSet cs, const double *__restrict__ LA, const double 
 }
 
 __device__ __forceinline__ bool viterbi_hoist_unsafe(double sstar, double le, double M);
+// |M| < 2^36 (false for inf and NaN): with a screen-proven margin the hoist is then safe
+__device__ __forceinline__ bool viterbi_small_for_hoist(double M) {
+    return ((unsigned)__double2hiint(M) & 0x7fffffffu) < 0x42300000u;
+}
 
 // ---------------------------------------------------------------------------------
 // Viterbi forward sweep for MANY chains (K <= 32): verify the cached pointer first.
@@ -1753,6 +1757,13 @@ viterbi_check_kernel(ChainSet cs, const double *__restrict__ LA, const double *_
 // that s_p is the strict, unique maximum of the reference's sums — the cached pointer is
 // np.argmax's answer — and the column's omega is then formed exactly as the reference does,
 // in FP64, from that pointer: (omega_p + log a_pj) + log e_j, with the usual hoisting test.
+// The same margin proves that the emission add can be hoisted (HOIST_SMALL): the real sums obey
+// s_i <= s_p - (2^-14 - 2 * 1.53e-5 - 2e-10) < s_p - 3.0e-5 for every i != p, and when
+// |M| = |fl(s_p + log e_j)| < 2^36 doubles around s_p + log e_j are at most 2^-16 apart (the
+// binade below 2^37), so fl(s_i + log e_j) <= s_i + log e_j + 2^-17 < s_p + log e_j - 2^-17 <= M:
+// no other predecessor can tie with p after the add, which is all viterbi_hoist_unsafe asks.
+// So the hot path tests the exponent of M (two integer instructions) instead of forming
+// fl(pred(s_p) + log e_j); the literal test runs out of line with the FP64 check.
 // A margin inside the band (ties and near-ties) is decided by the FP64 check of
 // viterbi_check_kernel, out of line; a lost pointer, an unsafe hoist, magnitudes beyond the
 // bound or NaN by the exact FP64 column (viterbi_full_column).  Bit-identical paths by
@@ -1787,6 +1798,23 @@ __device__ __forceinline__ float max3_f32(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
+}
+
+// maximum of N floats by three-input maxima arranged as a tree
+template <int N>
+__device__ __forceinline__ float max_tree3(const float (&v)[N]) {
+    if constexpr (N == 1) return v[0];
+    else if constexpr (N == 2) return fmaxf(v[0], v[1]);
+    else {
+        constexpr int M = (N + 2) / 3;
+        float w[M];
+#pragma unroll
+        for (int g = 0; g < M; ++g) {
+            const int a = 3 * g;
+            w[g] = (a + 2 < N) ? max3_f32(v[a], v[a + 1], v[a + 2]) : (a + 1 < N) ? fmaxf(v[a], v[a + 1]) : v[a];
+        }
+        return max_tree3<M>(w);
+    }
 }
 
 #ifndef ITR_VCHK32_MINB
@@ -1830,20 +1858,23 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
     for (int c = next_chain(cs, lane); c < n_chains; c = next_chain(cs, lane)) {
         const int blk = cs.order[c];
         const int64_t beg = cs.off[blk], T = cs.off[blk + 1] - beg;
-        const SymTile st{cs.sym + beg, T};
+        // symbols are read straight from HBM/L1, a few columns ahead (the buffer is padded by 64
+        // entries, so the read-ahead past a block's end stays inside it and yields valid symbols):
+        // one load per column instead of the five ALU instructions of a register tile + shuffle
+        const uint16_t *spt = cs.sym + beg;
         uint8_t *bpt = bp + (size_t)beg * KP + lane + KP;        // row of column t = 1
 
         int p = lane;                                            // cached pointer: "stay"
         double la_p = __ldg(LA + (size_t)lane * KP + lane);
-        float laf_p = (float)la_p;
+        float laf_p = la_ok ? (float)la_p : -CUDART_INF_F;      // (a column of log a beyond the bound never passes the screen)
         load_column_without(p);
-        unsigned vcur = st.load(0, lane), vnxt = st.load(32, lane);
         double om = __ldg(OM0 + (size_t)blk * KP + lane);
         double ref = __shfl_sync(FULL, om, 0);
-        double e1 = __ldg(etl + __shfl_sync(FULL, vcur, 1) * KP), e2 = __ldg(etl + __shfl_sync(FULL, vcur, 2) * KP);
-        unsigned vpre = tile_symbol(vcur, vnxt, 3);              // symbol of the column two ahead
+        double e1 = __ldg(etl + (size_t)__ldg(spt + 1) * KP), e2 = __ldg(etl + (size_t)__ldg(spt + 2) * KP);
+        unsigned v3 = __ldg(spt + 3), v4 = __ldg(spt + 4);       // symbols of the columns two and three ahead
+        spt += 5;
         int buf = 0;
-        auto column = [&](int s32) {
+        auto column = [&]() {
             double *xb = xs + buf * KP;
             float *fb = fs + buf * KP;
             const float d = (float)__dsub_rn(om, ref);
@@ -1851,32 +1882,38 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             fb[lane] = d;
             __syncwarp();
             buf ^= 1;
-            const double e3 = __ldg(etl + vpre * KP);
-            vpre = tile_symbol(vcur, vnxt, s32 + 4);
+            const double e3 = __ldg(etl + v3 * KP);
+            v3 = v4;
+            v4 = __ldg(spt++);
             // exact part: the reference's two adds for the cached pointer
             const double s_p = __dadd_rn(xb[p], la_p);
             double M = __dadd_rn(s_p, e1);
             // screen: is any other predecessor within the band of s_p?
             const float fp = fb[p] + laf_p;
             const ulonglong2 *f4 = reinterpret_cast<const ulonglong2 *>(fb);
-            float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+            float sv[KT];
 #pragma unroll
             for (int i = 0; i < KT; i += 4) {
                 const ulonglong2 q = f4[i / 4];
                 const unsigned long long r01 = add_f32x2(q.x, laf2[i / 2]), r23 = add_f32x2(q.y, laf2[i / 2 + 1]);
-                m0 = max3_f32(m0, __uint_as_float((unsigned)r01), __uint_as_float((unsigned)(r01 >> 32)));
-                m1 = max3_f32(m1, __uint_as_float((unsigned)r23), __uint_as_float((unsigned)(r23 >> 32)));
+                sv[i] = __uint_as_float((unsigned)r01);
+                sv[i + 1] = __uint_as_float((unsigned)(r01 >> 32));
+                sv[i + 2] = __uint_as_float((unsigned)r23);
+                sv[i + 3] = __uint_as_float((unsigned)(r23 >> 32));
             }
-            const float other = fmaxf(m0, m1);
+            const float other = max_tree3<KT>(sv);               // (three-input maxima as a tree: depth 4 instead of 7)
             const double ref_next = xb[0];
             // the bound on |d| is a property of the column: every live lane votes on its own d
             const bool d_ok = (lane >= K) | (d == -CUDART_INF_F) | (fabsf(d) < BOUND);
-            const bool trusted = __all_sync(FULL, d_ok) & la_ok;
-            const bool proven = trusted & (fp - other > BAND);
-            const bool unsafe = viterbi_hoist_unsafe(s_p, e1, M);
-            if (__builtin_expect(__any_sync(FULL, (lane < K) & (!proven | unsafe)), 0)) {
+            const bool trusted = __all_sync(FULL, d_ok);
+            // A proven margin also proves the hoist (HOIST_SMALL, see the header): two instructions
+            // instead of the sixteen of viterbi_hoist_unsafe on the ALU pipe that binds this kernel.
+            const bool proven = trusted & (fp - other > BAND) & viterbi_small_for_hoist(M);
+            if (__builtin_expect(__any_sync(FULL, (lane < K) & !proven), 0)) {
                 // band, bound or hoist: the FP64 check decides whether the pointers stand
-                bool redo = __any_sync(FULL, (lane < K) & unsafe);
+                // (a pointer that lost by more than the band goes straight to the exact column — that is
+                // always right, so the shortcut needs no bound; nearly every column that gets here is one)
+                bool redo = __any_sync(FULL, (lane < K) & ((fp - other < -BAND) | viterbi_hoist_unsafe(s_p, e1, M)));
                 if (!redo) redo = __any_sync(FULL, (lane < K) & viterbi_pointer_beaten<KT>(xb, LA + lane, p, s_p));
                 if (redo) {
                     const ScanResult r = viterbi_full_column<KT>(xb, LA + lane, K, K4, e1);
@@ -1884,7 +1921,7 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
                     if (r.arg != p) {
                         p = r.arg;
                         la_p = __ldg(LA + (size_t)p * KP + lane);
-                        laf_p = (float)la_p;
+                        laf_p = la_ok ? (float)la_p : -CUDART_INF_F;
                         load_column_without(p);
                     }
                 }
@@ -1896,15 +1933,8 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             e1 = e2;
             e2 = e3;
         };
-        int64_t t0 = 0;
-        for (; t0 + 32 < T; t0 += 32) {
 #pragma unroll 2
-            for (int s32 = 0; s32 < 32; ++s32) column(s32);
-            vcur = vnxt;
-            vnxt = st.load(t0 + 64, lane);
-        }
-#pragma unroll 1
-        for (int s32 = 0; t0 + s32 + 1 < T; ++s32) column(s32);
+        for (int64_t t = 1; t < T; ++t) column();
         // first argmax of omega_{T-1}
         double best = (lane < K) ? om : -CUDART_INF;
         int bidx = (lane < K) ? lane : 0x7fffffff;
@@ -2182,7 +2212,7 @@ struct StreamCfg {
 };
 
 #ifndef ITR_STR8_MINB
-#define ITR_STR8_MINB 1
+#define ITR_STR8_MINB 2
 #endif
 template <int KT, int NWARPS>
 __global__ void __launch_bounds__(32 * NWARPS, NWARPS == 8 ? ITR_STR8_MINB : 1)
@@ -2405,10 +2435,10 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                             m1 = max3_f32(m1, __uint_as_float((unsigned)r23), __uint_as_float((unsigned)(r23 >> 32)));
                         }
                         const bool d_ok = (lane >= K) | (d == -CUDART_INF_F) | (fabsf(d) < 64.f);
-                        const bool proven = __all_sync(FULL, d_ok) & la_ok & (fp - fmaxf(m0, m1) > 6.103515625e-5f);
-                        const bool unsafe = viterbi_hoist_unsafe(s_p, le, M);
-                        if (__any_sync(FULL, (lane < K) & (!proven | unsafe))) {
-                            bool redo = __any_sync(FULL, (lane < K) & unsafe);
+                        const bool proven = __all_sync(FULL, d_ok) & la_ok & (fp - fmaxf(m0, m1) > 6.103515625e-5f) &
+                                            viterbi_small_for_hoist(M);
+                        if (__any_sync(FULL, (lane < K) & !proven)) {
+                            bool redo = __any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(s_p, le, M));
                             if (!redo) redo = __any_sync(FULL, (lane < K) & viterbi_pointer_beaten<KT>(xin, LA + lane, myp, s_p));
                             if (redo) {
                                 const ScanResult r = viterbi_full_column<KT>(xin, LA + lane, K, K4, le);
