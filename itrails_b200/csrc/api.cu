@@ -57,6 +57,7 @@ struct itr_ctx {
     int64_t *d_chunk_off = nullptr;
     int32_t *d_chunk_blk = nullptr;
     unsigned int *d_queue = nullptr;
+    unsigned long long *d_tile_ticket = nullptr;     // group tickets of posterior_tiles_mma_kernel
     size_t cap_sym = 0, cap_off = 0, cap_order = 0, cap_chunk_off = 0, cap_chunk_blk = 0;
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_order;
@@ -233,6 +234,7 @@ extern "C" int itr_create(int device, itr_ctx **out) {
         if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     if ((e = cudaMalloc((void **)&ctx->d_queue, 64 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_tile_ticket, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     // symbol digit table: read_data.py:6-24 ordering
     {
         std::vector<uint16_t> dig(NSYM);
@@ -268,7 +270,8 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
                     ctx->d_LEt, ctx->d_OM0, ctx->d_tmp, ctx->d_bp, ctx->d_comp, ctx->d_chunk_end,
                     ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
                     ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar, ctx->d_Pb, ctx->d_ck_a, ctx->d_ck_b,
-                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile, ctx->d_tile_info, ctx->d_ls_ll, ctx->d_ls_post};
+                    ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile, ctx->d_tile_info, ctx->d_ls_ll, ctx->d_ls_post,
+                    ctx->d_tile_ticket};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -615,6 +618,7 @@ static Geometry geometry(const itr_ctx *ctx, int64_t n_chains, int max_warps_per
 // be executed by a copy engine, where it queues behind a posterior download in progress
 // (measured: the log-likelihood of a step started only after the 2 GB transfer, +5.7 ms).
 __global__ void zero_u32_kernel(unsigned int *p) { *p = 0u; }
+__global__ void zero_u64_kernel(unsigned long long *p) { *p = 0ull; }
 static inline void reset_queue(unsigned int *q, cudaStream_t st) { zero_u32_kernel<<<1, 1, 0, st>>>(q); }
 
 static ChainSet chain_set(const itr_ctx *ctx, int n_sets, int slot = 0) {
@@ -1146,7 +1150,7 @@ static void launch_checkpoint_sweep(itr_ctx *ctx, int dir, const ChainSet &cs, c
 // tensor cores, eight tiles per warp in lock step (posterior_tiles_mma_kernel); the
 // partial last tile of each block — and everything when K > 28 or ITR_POST_TILES=fma —
 // through the one-warp-per-tile FMA kernel.
-static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, int64_t b1) {
+static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, int64_t b1, bool dynamic_ok = false) {
     const int64_t t0 = ctx->h_tile_off[b0], t1 = ctx->h_tile_off[b1];
     if (t1 <= t0) return cudaSuccess;
     const int K = ctx->K, KP = ctx->KP;
@@ -1161,6 +1165,11 @@ static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, 
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024 - 1024) / (shm + 1024)));
         const int64_t groups = (t1 - t0 + 3) / 4;
         const unsigned gm = (unsigned)std::min<int64_t>((groups + MMA_WARPS - 1) / MMA_WARPS, (int64_t)sms * per_sm);
+        // more groups than warps: tickets instead of a static split (see the kernel); the launches
+        // that take this path are ordered on one stream, so one counter, zeroed in-stream, serves
+        static const char *stat = getenv("ITR_POST_STATIC");        // experiments
+        unsigned long long *tk = (dynamic_ok && !stat && groups > (int64_t)gm * MMA_WARPS) ? ctx->d_tile_ticket : nullptr;
+        if (tk) zero_u64_kernel<<<1, 1, 0, st>>>(tk);
 #define PTM(KT)                                                                                                          \
     do {                                                                                                                 \
         if constexpr (KT <= 28) {                                                                                        \
@@ -1168,7 +1177,7 @@ static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, 
             if (e == cudaSuccess)                                                                                        \
                 posterior_tiles_mma_kernel<KT><<<gm, 32 * MMA_WARPS, shm, st>>>(ctx->d_sym, ctx->d_tile_info, t0, t1, \
                                                                          ctx->d_A, ctx->d_PI, ctx->d_Et, ctx->d_ck_a, ctx->d_ck_b, K,   \
-                                                                         ctx->d_post);                                   \
+                                                                         ctx->d_post, tk);                               \
         }                                                                                                                \
     } while (0)
         ITR_SWITCH_KT(K, PTM)
@@ -1311,7 +1320,7 @@ extern "C" int itr_posterior(itr_ctx *ctx, double *post) {
                 for (int r = 0; r < n_ranges; ++r) {
                     const int64_t b0 = (int64_t)nb * r / n_ranges, b1 = (int64_t)nb * (r + 1) / n_ranges;
                     if (b1 <= b0) continue;
-                    CK(launch_post_tiles(ctx, st, b0, b1));
+                    CK(launch_post_tiles(ctx, st, b0, b1, true));
                     if (want_ranges > 0) {
                         while (ctx->range_events.size() <= ctx->range_col_end.size()) {
                             cudaEvent_t e = nullptr;

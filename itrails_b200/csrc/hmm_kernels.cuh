@@ -923,7 +923,7 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const unsigned long
                            int64_t g_begin, int64_t g_end, const double *__restrict__ A,
                            const double *__restrict__ PI, const double *__restrict__ Et,
                            const double *__restrict__ ck_a, const double *__restrict__ ck_b, int K,
-                           double *__restrict__ post) {
+                           double *__restrict__ post, unsigned long long *__restrict__ ticket) {
     static_assert(KT % 4 == 0 && KT <= 32, "KT is K rounded up to a multiple of 4");
     constexpr int KP = 32, NQ = KT / 4, NC = (KT + 7) / 8, HALF = PTILE / 2;
     extern __shared__ __align__(16) double smem[];
@@ -952,22 +952,39 @@ posterior_tiles_mma_kernel(const uint16_t *__restrict__ sym, const unsigned long
     }
     const double *etc = Et + c;
 
+    // Groups of four tiles are handed out by a ticket counter (ticket != nullptr): inside a step
+    // this kernel starts while the Viterbi sweep still holds most SMs, so its CTAs become
+    // resident one by one over tens of milliseconds — with a static round-robin split the CTAs
+    // that start last still own a full share and the launch ends a whole share after the
+    // sweep (82 ms inside the step against 40 ms alone); with tickets whoever is resident works.
+    // The ticket of the group after next is drawn at the top of a group, so the atomic's round
+    // trip is hidden behind ~2 000 cycles of work.
     const int64_t stride = (int64_t)gridDim.x * MMA_WARPS * 4;
-    int64_t g0 = g_begin + ((int64_t)blockIdx.x * MMA_WARPS + warp) * 4;
+    auto next_group = [&](int64_t cur) -> int64_t {
+        if (ticket == nullptr) return cur + stride;
+        unsigned long long tk = 0ull;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);
+        tk = __shfl_sync(FULL, tk, 0);
+        return g_begin + 4 * (int64_t)tk;
+    };
+    int64_t g0 = ticket ? next_group(0) : g_begin + ((int64_t)blockIdx.x * MMA_WARPS + warp) * 4;
+    int64_t g1 = g0 < g_end ? next_group(g0) : g_end;
     // the tile word of the NEXT group is fetched a whole group ahead, and with it the first
     // symbols of that tile: the chain word -> symbol -> emission row is off the critical path
     auto tile_word = [&](int64_t gg0) { return gg0 + tl < g_end ? __ldg(tile_info + gg0 + tl) : (__ldg(tile_info + g_end - 1) & ~TILE_FULL); };
     unsigned long long w_next = g0 < g_end ? tile_word(g0) : 0ull;
-    for (; g0 < g_end; g0 += stride) {
+    for (int64_t g2 = g_end; g0 < g_end; g0 = g1, g1 = g2) {
         const unsigned long long w = w_next;
         const int64_t g = min(g0 + tl, g_end - 1);
-        if (g0 + stride < g_end) {
-            w_next = tile_word(g0 + stride);
+        g2 = g_end;
+        if (g1 < g_end) {
+            w_next = tile_word(g1);
             // next group's checkpoint vectors (256 B each, two lines): into L2 now
             if (c < 2) {
-                const double *nk = (bwd ? ck_b : ck_a) + (size_t)min(g + stride, g_end - 1) * KP + 16 * c;
+                const double *nk = (bwd ? ck_b : ck_a) + (size_t)min(g1 + tl, g_end - 1) * KP + 16 * c;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nk));
             }
+            g2 = next_group(g1);
         }
         const bool full = (w & TILE_FULL) != 0;           // tiles that are stored
         const long long col0 = (long long)(w & TILE_COL_MASK);
