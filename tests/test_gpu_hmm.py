@@ -219,6 +219,28 @@ def test_viterbi_kernel_variants_agree(engine, variant, monkeypatch):
         assert np.array_equal(p, r)
 
 
+@pytest.mark.parametrize("variant", ["check", "stream", "stream8"])
+@pytest.mark.parametrize("shift", [-7.0e10, -2.0 ** 36 + 3000.0, -1.0e300])
+def test_viterbi_screen_refuses_the_hoist_shortcut_for_huge_omega(engine, variant, shift, monkeypatch):
+    """The FP32 screen proves the emission hoist only for |omega| < 2^36.  With
+    omega_0 shifted beyond that (or drifting across 2^36 inside the block, or near the top of the
+    double range, where doubles are far apart and sums collapse into ties) the exponent test must
+    send every column to the literal hoisting test; paths stay bit-exact against the C oracle."""
+    monkeypatch.setenv("ITR_VITERBI", variant)
+    m = golden("model_3_3_example.npz")
+    a, b, pi = m["a"], m["b"], m["pi"]
+    rng = np.random.default_rng(1234)
+    V_lst = [ho.sample_block(a, b, pi, T, rng, p_n=0.02) for T in (6000, 700, 1, 33)]
+    V_lst += [rng.integers(0, 625, size=900)]
+    engine.load_blocks(V_lst)
+    engine.set_model(a, b, pi)
+    LA, LE, om0 = _tables(a, b, pi, V_lst)
+    om0 = om0 + shift
+    path = engine.split(engine.viterbi(LA, LE, om0))
+    for p, r in zip(path, hoc.viterbi_blocks(LA, LE, om0, V_lst)):
+        assert np.array_equal(p, r)
+
+
 def test_many_blocks_and_async_overlap(engine):
     """700 short blocks (one-warp sweep, several chains per warp through the work queue)
     and the asynchronous mode: the three recursions enqueued back to back give the
