@@ -56,6 +56,7 @@ struct itr_ctx {
     int32_t *d_order = nullptr;
     int64_t *d_chunk_off = nullptr;
     int32_t *d_chunk_blk = nullptr;
+    bool comp_done = false;                   // the Viterbi sweep of the current call wrote d_comp itself
     unsigned int *d_queue = nullptr;
     unsigned long long *d_tile_ticket = nullptr;     // group tickets of posterior_tiles_mma_kernel
     size_t cap_sym = 0, cap_off = 0, cap_order = 0, cap_chunk_off = 0, cap_chunk_blk = 0;
@@ -861,9 +862,10 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
         const int wps32 = w32 ? std::max(4, atoi(w32)) : 12;
         g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n_blocks + 3) / 4, (int64_t)sms * (wps32 / 4)));
         const size_t sh32 = (size_t)g.warps * 3 * KP * sizeof(double);
-#define VCHK32(KT) viterbi_check32_kernel<KT><<<g.grid, g.warps * 32, sh32, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final)
+#define VCHK32(KT) viterbi_check32_kernel<KT><<<g.grid, g.warps * 32, sh32, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final, ctx->d_chunk_off, ctx->d_comp)
         ITR_SWITCH_KT(K, VCHK32)
 #undef VCHK32
+        ctx->comp_done = true;          // this sweep writes the traceback's chunk composites itself
         return;
     }
 #define VIT_REG(KT)                                                        \
@@ -1070,6 +1072,7 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
     pad_kernel<<<blocks_for((size_t)nb * KP, 256), 256, 0, st>>>(t_om, ctx->d_OM0, (int)nb, 1, K, 1, KP, ninf);
     ctx->launches += 3;
     phase_begin(ctx, ITR_PH_VITERBI_FWD, st);
+    ctx->comp_done = false;
     launch_viterbi_forward(ctx, st);
     phase_end(ctx, ITR_PH_VITERBI_FWD, st);
     phase_begin(ctx, ITR_PH_VITERBI_TRACE, st);
@@ -1078,8 +1081,9 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
         size_t sh1 = 0, sh2 = 0;
         CK(chunk_smem(viterbi_compose_kernel, (size_t)VCHUNK * KP, &w1, &sh1));
         CK(chunk_smem(viterbi_traceback_kernel, (size_t)VCHUNK * KP + VCHUNK, &w2, &sh2));
-        viterbi_compose_kernel<<<blocks_for((size_t)ctx->n_chunks, w1), w1 * 32, sh1, st>>>(
-            ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, KP, K, ctx->n_chunks, ctx->d_comp);
+        if (!ctx->comp_done)
+            viterbi_compose_kernel<<<blocks_for((size_t)ctx->n_chunks, w1), w1 * 32, sh1, st>>>(
+                ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, KP, K, ctx->n_chunks, ctx->d_comp);
         viterbi_boundary_kernel<<<blocks_for((size_t)nb, VB_WARPS), 32 * VB_WARPS, 0, st>>>(ctx->d_off, ctx->d_chunk_off, ctx->d_comp,
                                                                             ctx->d_final, KP, (int)nb, ctx->d_chunk_end);
         viterbi_traceback_kernel<<<blocks_for((size_t)ctx->n_chunks, w2), w2 * 32, sh2, st>>>(

@@ -1841,7 +1841,8 @@ template <int KT>
 __global__ void __launch_bounds__(128, ITR_VCHK32_MINB)
 viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                        const double *__restrict__ OM0, int K,
-                       uint8_t *__restrict__ bp, int32_t *__restrict__ final_state) {
+                       uint8_t *__restrict__ bp, int32_t *__restrict__ final_state,
+                       const int64_t *__restrict__ chunk_off, uint8_t *__restrict__ comp) {
     constexpr int KP = 32;
     constexpr float BAND = 6.103515625e-5f, BOUND = 64.f;      // 2^-14 and the magnitude bound, see above
     extern __shared__ __align__(16) double smem[];
@@ -1922,11 +1923,11 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             const double ref_next = xb[0];
             // the bound on |d| is a property of the column: every live lane votes on its own d
             const bool d_ok = (lane >= K) | (d == -CUDART_INF_F) | (fabsf(d) < BOUND);
-            const bool trusted = __all_sync(FULL, d_ok);
             // A proven margin also proves the hoist (HOIST_SMALL, see the header): two instructions
-            // instead of the sixteen of viterbi_hoist_unsafe on the ALU pipe that binds this kernel.
-            const bool proven = trusted & (fp - other > BAND) & viterbi_small_for_hoist(M);
-            if (__builtin_expect(__any_sync(FULL, (lane < K) & !proven), 0)) {
+            // instead of the sixteen of viterbi_hoist_unsafe.  One vote serves both questions: a lane
+            // whose d is out of bounds sends the whole warp to the FP64 path, as an unproven lane does.
+            const bool proven = (fp - other > BAND) & viterbi_small_for_hoist(M);
+            if (__builtin_expect(__any_sync(FULL, ((lane < K) & !proven) | !d_ok), 0)) {
                 // band, bound or hoist: the FP64 check decides whether the pointers stand
                 // (a pointer that lost by more than the band goes straight to the exact column — that is
                 // always right, so the shortcut needs no bound; nearly every column that gets here is one)
@@ -1950,8 +1951,22 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             e1 = e2;
             e2 = e3;
         };
+        // The traceback's chunk composites ("state at the last column of the previous chunk, given
+        // state j at this chunk's last column", viterbi_compose_kernel) fall out of the sweep:
+        // F_t[j] = F_{t-1}[p_t[j]] is one shuffle per column, and the 8 GB re-read of the
+        // backpointers by the compose kernel disappears.
+        const int64_t cbase = chunk_off[blk];
+        int64_t t = 1;
+        for (int64_t c0 = 0; c0 * VCHUNK < T; ++c0) {
+            const int64_t tend = min((c0 + 1) * (int64_t)VCHUNK, T);
+            int F = lane;
 #pragma unroll 2
-        for (int64_t t = 1; t < T; ++t) column();
+            for (; t < tend; ++t) {
+                column();
+                F = __shfl_sync(FULL, F, p);
+            }
+            if (c0 > 0) comp[(size_t)(cbase + c0) * KP + lane] = (uint8_t)F;
+        }
         // first argmax of omega_{T-1}
         double best = (lane < K) ? om : -CUDART_INF;
         int bidx = (lane < K) ? lane : 0x7fffffff;
@@ -2452,9 +2467,8 @@ viterbi_stream_kernel(ChainSet cs, const double *__restrict__ LA, const double *
                             m1 = max3_f32(m1, __uint_as_float((unsigned)r23), __uint_as_float((unsigned)(r23 >> 32)));
                         }
                         const bool d_ok = (lane >= K) | (d == -CUDART_INF_F) | (fabsf(d) < 64.f);
-                        const bool proven = __all_sync(FULL, d_ok) & la_ok & (fp - fmaxf(m0, m1) > 6.103515625e-5f) &
-                                            viterbi_small_for_hoist(M);
-                        if (__any_sync(FULL, (lane < K) & !proven)) {
+                        const bool proven = la_ok & (fp - fmaxf(m0, m1) > 6.103515625e-5f) & viterbi_small_for_hoist(M);
+                        if (__any_sync(FULL, ((lane < K) & !proven) | !d_ok)) {
                             bool redo = __any_sync(FULL, (lane < K) & viterbi_hoist_unsafe(s_p, le, M));
                             if (!redo) redo = __any_sync(FULL, (lane < K) & viterbi_pointer_beaten<KT>(xin, LA + lane, myp, s_p));
                             if (redo) {
