@@ -1888,9 +1888,12 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
         load_column_without(p);
         double om = __ldg(OM0 + (size_t)blk * KP + lane);
         double ref = __shfl_sync(FULL, om, 0);
-        double e1 = __ldg(etl + (size_t)__ldg(spt + 1) * KP), e2 = __ldg(etl + (size_t)__ldg(spt + 2) * KP);
-        unsigned v3 = __ldg(spt + 3), v4 = __ldg(spt + 4);       // symbols of the columns two and three ahead
-        spt += 5;
+        // (one column of read-ahead for the emission row, one more for its symbol: a column takes
+        // hundreds of cycles, an L1 hit forty — and with the loop unrolled by two a pipeline of depth
+        // one needs no register moves)
+        double e1 = __ldg(etl + (size_t)__ldg(spt + 1) * KP);
+        unsigned v2 = __ldg(spt + 2);
+        spt += 3;
         int buf = 0;
         auto column = [&]() {
             double *xb = xs + buf * KP;
@@ -1900,9 +1903,8 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             fb[lane] = d;
             __syncwarp();
             buf ^= 1;
-            const double e3 = __ldg(etl + v3 * KP);
-            v3 = v4;
-            v4 = __ldg(spt++);
+            const double e2 = __ldg(etl + v2 * KP);
+            v2 = __ldg(spt++);
             // exact part: the reference's two adds for the cached pointer
             const double s_p = __dadd_rn(xb[p], la_p);
             double M = __dadd_rn(s_p, e1);
@@ -1949,7 +1951,6 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             *bpt = (uint8_t)p;
             bpt += KP;
             e1 = e2;
-            e2 = e3;
         };
         // The traceback's chunk composites ("state at the last column of the previous chunk, given
         // state j at this chunk's last column", viterbi_compose_kernel) fall out of the sweep:
