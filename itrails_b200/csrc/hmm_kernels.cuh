@@ -1894,22 +1894,23 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
         double e1 = __ldg(etl + (size_t)__ldg(spt + 1) * KP);
         unsigned v2 = __ldg(spt + 2);
         spt += 3;
-        int buf = 0;
-        auto column = [&]() {
-            double *xb = xs + buf * KP;
-            float *fb = fs + buf * KP;
+        // omega and its differences are double buffered (one __syncwarp per column); the loop
+        // below names the buffers explicitly, so every shared-memory address of a column is a
+        // loop constant — including the pointer's own entries, cached per buffer
+        const double *xp0 = xs + p, *xp1 = xs + KP + p;
+        const float *fq0 = fs + p, *fq1 = fs + KP + p;
+        auto column = [&](double *xb, float *fb, const double *xpp, const float *fpp) {
             const float d = (float)__dsub_rn(om, ref);
             xb[lane] = om;
             fb[lane] = d;
             __syncwarp();
-            buf ^= 1;
             const double e2 = __ldg(etl + v2 * KP);
             v2 = __ldg(spt++);
             // exact part: the reference's two adds for the cached pointer
-            const double s_p = __dadd_rn(xb[p], la_p);
+            const double s_p = __dadd_rn(*xpp, la_p);
             double M = __dadd_rn(s_p, e1);
             // screen: is any other predecessor within the band of s_p?
-            const float fp = fb[p] + laf_p;
+            const float fp = *fpp + laf_p;
             const ulonglong2 *f4 = reinterpret_cast<const ulonglong2 *>(fb);
             float sv[KT];
 #pragma unroll
@@ -1943,6 +1944,8 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
                         la_p = __ldg(LA + (size_t)p * KP + lane);
                         laf_p = la_ok ? (float)la_p : -CUDART_INF_F;
                         load_column_without(p);
+                        xp0 = xs + p, xp1 = xs + KP + p;
+                        fq0 = fs + p, fq1 = fs + KP + p;
                     }
                 }
             }
@@ -1956,16 +1959,32 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
         // state j at this chunk's last column", viterbi_compose_kernel) fall out of the sweep:
         // F_t[j] = F_{t-1}[p_t[j]] is one shuffle per column, and the 8 GB re-read of the
         // backpointers by the compose kernel disappears.
+        // Column 1 goes first, alone, in buffer 0: after it every chunk but a block's last holds an
+        // even number of columns, so the pairs (buffer 1, buffer 0) never straddle a chunk.
         const int64_t cbase = chunk_off[blk];
         int64_t t = 1;
+        int F = lane;
+        if (t < T) {
+            column(xs, fs, xp0, fq0);
+            F = __shfl_sync(FULL, F, p);
+            ++t;
+        }
         for (int64_t c0 = 0; c0 * VCHUNK < T; ++c0) {
             const int64_t tend = min((c0 + 1) * (int64_t)VCHUNK, T);
-            int F = lane;
-#pragma unroll 2
-            for (; t < tend; ++t) {
-                column();
+            if (c0 > 0) F = lane;
+            const int n = (int)(tend - t);
+#pragma unroll 1
+            for (int i = 0; i + 1 < n; i += 2) {
+                column(xs + KP, fs + KP, xp1, fq1);
+                F = __shfl_sync(FULL, F, p);
+                column(xs, fs, xp0, fq0);
                 F = __shfl_sync(FULL, F, p);
             }
+            if (n & 1) {                                   // (a block's last chunk only)
+                column(xs + KP, fs + KP, xp1, fq1);
+                F = __shfl_sync(FULL, F, p);
+            }
+            t = tend;
             if (c0 > 0) comp[(size_t)(cbase + c0) * KP + lane] = (uint8_t)F;
         }
         // first argmax of omega_{T-1}
