@@ -1834,6 +1834,10 @@ __device__ __forceinline__ float max_tree3(const float (&v)[N]) {
     }
 }
 
+#ifndef ITR_VCHK32_PAIRS
+#define ITR_VCHK32_PAIRS 1      /* column pairs per loop trip (2: same speed, twice the code) */
+#endif
+constexpr int VCHK32_PAIRS = ITR_VCHK32_PAIRS;
 #ifndef ITR_VCHK32_MINB
 #define ITR_VCHK32_MINB 3
 #endif
@@ -1973,7 +1977,7 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
             const int64_t tend = min((c0 + 1) * (int64_t)VCHUNK, T);
             if (c0 > 0) F = lane;
             const int n = (int)(tend - t);
-#pragma unroll 1
+#pragma unroll VCHK32_PAIRS
             for (int i = 0; i + 1 < n; i += 2) {
                 column(xs + KP, fs + KP, xp1, fq1);
                 F = __shfl_sync(FULL, F, p);
