@@ -1090,7 +1090,7 @@ extern "C" int itr_viterbi(itr_ctx *ctx, const double *log_a, const double *log_
             ctx->d_off, ctx->d_chunk_off, ctx->d_chunk_blk, ctx->d_bp, ctx->d_chunk_end, KP, ctx->n_chunks, ctx->d_path);
     }
     phase_end(ctx, ITR_PH_VITERBI_TRACE, st);
-    ctx->launches += 3;
+    ctx->launches += ctx->comp_done ? 2 : 3;
     CK(cudaGetLastError());
     ctx->have_path = true;
     if (path) CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)ctx->n_cols, cudaMemcpyDeviceToHost, st));
@@ -1173,7 +1173,10 @@ static cudaError_t launch_post_tiles(itr_ctx *ctx, cudaStream_t st, int64_t b0, 
         // that take this path are ordered on one stream, so one counter, zeroed in-stream, serves
         static const char *stat = getenv("ITR_POST_STATIC");        // experiments
         unsigned long long *tk = (dynamic_ok && !stat && groups > (int64_t)gm * MMA_WARPS) ? ctx->d_tile_ticket : nullptr;
-        if (tk) zero_u64_kernel<<<1, 1, 0, st>>>(tk);
+        if (tk) {
+            zero_u64_kernel<<<1, 1, 0, st>>>(tk);
+            ctx->launches += 1;
+        }
 #define PTM(KT)                                                                                                          \
     do {                                                                                                                 \
         if constexpr (KT <= 28) {                                                                                        \
