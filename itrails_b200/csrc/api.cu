@@ -59,6 +59,7 @@ struct itr_ctx {
     bool comp_done = false;                   // the Viterbi sweep of the current call wrote d_comp itself
     unsigned int *d_queue = nullptr;
     unsigned long long *d_tile_ticket = nullptr;     // group tickets of posterior_tiles_mma_kernel
+    float *d_LAfT = nullptr;                         // float(log a) transposed, 32 x 32 (viterbi_check32_kernel)
     size_t cap_sym = 0, cap_off = 0, cap_order = 0, cap_chunk_off = 0, cap_chunk_blk = 0;
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_order;
@@ -236,6 +237,7 @@ extern "C" int itr_create(int device, itr_ctx **out) {
     }
     if ((e = cudaMalloc((void **)&ctx->d_queue, 64 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_tile_ticket, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_LAfT, 32 * 32 * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
     // symbol digit table: read_data.py:6-24 ordering
     {
         std::vector<uint16_t> dig(NSYM);
@@ -272,7 +274,7 @@ extern "C" void itr_destroy(itr_ctx *ctx) {
                     ctx->d_path, ctx->d_final, ctx->d_post, ctx->d_beta, ctx->d_rep, ctx->d_sP, ctx->d_hist,
                     ctx->d_isrun, ctx->d_runinfo, ctx->d_P, ctx->d_ebar, ctx->d_Pb, ctx->d_ck_a, ctx->d_ck_b,
                     ctx->d_tile_off, ctx->d_tile_blk, ctx->d_part_tile, ctx->d_tile_info, ctx->d_ls_ll, ctx->d_ls_post,
-                    ctx->d_tile_ticket};
+                    ctx->d_tile_ticket, ctx->d_LAfT};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < ITR_PH_COUNT; ++i) {
@@ -862,7 +864,9 @@ static void launch_viterbi_forward(itr_ctx *ctx, cudaStream_t st) {
         const int wps32 = w32 ? std::max(4, atoi(w32)) : 12;
         g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n_blocks + 3) / 4, (int64_t)sms * (wps32 / 4)));
         const size_t sh32 = (size_t)g.warps * 3 * KP * sizeof(double);
-#define VCHK32(KT) viterbi_check32_kernel<KT><<<g.grid, g.warps * 32, sh32, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final, ctx->d_chunk_off, ctx->d_comp)
+        la_float_transposed_kernel<<<1, 1024, 0, st>>>(ctx->d_LA, ctx->d_LAfT);
+        ctx->launches += 1;
+#define VCHK32(KT) viterbi_check32_kernel<KT><<<g.grid, g.warps * 32, sh32, st>>>(cs, ctx->d_LA, ctx->d_LEt, ctx->d_OM0, K, ctx->d_bp, ctx->d_final, ctx->d_chunk_off, ctx->d_comp, ctx->d_LAfT)
         ITR_SWITCH_KT(K, VCHK32)
 #undef VCHK32
         ctx->comp_done = true;          // this sweep writes the traceback's chunk composites itself

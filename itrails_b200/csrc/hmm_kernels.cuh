@@ -1817,6 +1817,12 @@ __device__ __forceinline__ float max3_f32(float a, float b, float c) {
     return r;
 }
 
+// LAfT[j][i] = float(log a[i][j]) (KP = 32): lane j's column of log a, contiguous, in the screen's precision
+__global__ void la_float_transposed_kernel(const double *__restrict__ LA, float *__restrict__ LAfT) {
+    const int j = threadIdx.x >> 5, i = threadIdx.x & 31;
+    LAfT[j * 32 + i] = (float)LA[i * 32 + j];
+}
+
 // maximum of N floats by three-input maxima arranged as a tree
 template <int N>
 __device__ __forceinline__ float max_tree3(const float (&v)[N]) {
@@ -1846,7 +1852,8 @@ __global__ void __launch_bounds__(128, ITR_VCHK32_MINB)
 viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double *__restrict__ LEt,
                        const double *__restrict__ OM0, int K,
                        uint8_t *__restrict__ bp, int32_t *__restrict__ final_state,
-                       const int64_t *__restrict__ chunk_off, uint8_t *__restrict__ comp) {
+                       const int64_t *__restrict__ chunk_off, uint8_t *__restrict__ comp,
+                       const float *__restrict__ LAfT) {
     constexpr int KP = 32;
     constexpr float BAND = 6.103515625e-5f, BOUND = 64.f;      // 2^-14 and the magnitude bound, see above
     extern __shared__ __align__(16) double smem[];
@@ -1860,12 +1867,22 @@ viterbi_check32_kernel(ChainSet cs, const double *__restrict__ LA, const double 
     // uses the packed FADD2 and the three-input FMNMX3 of sm_100: 28 instructions for 28
     // predecessors), the cached pointer's entry replaced by -inf
     unsigned long long laf2[KT / 2];
+    // (read from LAfT = float(log a) transposed, la_float_transposed_kernel: seven 16-byte loads per
+    // pointer change instead of 28 x (LDG.64 + F2F) — a pointer changes in 2.5 % of the columns)
     auto load_column_without = [&](int p) {
+        const float4 *row = reinterpret_cast<const float4 *>(LAfT + (size_t)lane * KP);
+        auto pack = [](float lo, float hi) {
+            return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+        };
 #pragma unroll
-        for (int i = 0; i < KT; i += 2) {
-            const float l0 = (i == p) ? -CUDART_INF_F : (float)__ldg(LA + (size_t)i * KP + lane);
-            const float l1 = (i + 1 == p) ? -CUDART_INF_F : (float)__ldg(LA + (size_t)(i + 1) * KP + lane);
-            laf2[i / 2] = (unsigned long long)__float_as_uint(l0) | ((unsigned long long)__float_as_uint(l1) << 32);
+        for (int i = 0; i < KT; i += 4) {
+            float4 v = __ldg(row + i / 4);
+            v.x = (i == p) ? -CUDART_INF_F : v.x;
+            v.y = (i + 1 == p) ? -CUDART_INF_F : v.y;
+            v.z = (i + 2 == p) ? -CUDART_INF_F : v.z;
+            v.w = (i + 3 == p) ? -CUDART_INF_F : v.w;
+            laf2[i / 2] = pack(v.x, v.y);
+            laf2[i / 2 + 1] = pack(v.z, v.w);
         }
     };
     // is every finite entry of this lane's column of log a inside the bound?  (-inf: that
