@@ -89,6 +89,11 @@ int itr_maf_read(const char *path, const char *const species[4], const char *ref
 void itr_maf_free(itr_maf *m);
 int64_t itr_maf_num_blocks(const itr_maf *m);
 int64_t itr_maf_num_columns(const itr_maf *m);
+/* Copies the symbols of all kept blocks (itr_maf_num_columns values) and / or the coordinates
+ * (itr_maf_coord_offsets()[itr_maf_num_coord_blocks] values) into the caller's arrays, with
+ * n_threads host threads (0: all); either pointer may be NULL.  Prefer it to the pointer
+ * accessors below, which concatenate inside the handle on first use. */
+int itr_maf_export(const itr_maf *m, uint16_t *sym_out, int64_t *coord_out, int n_threads);
 const uint16_t *itr_maf_symbols(const itr_maf *m);
 const int64_t *itr_maf_offsets(const itr_maf *m);
 int64_t itr_maf_num_coord_blocks(const itr_maf *m);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "itr_maf_free": (None, [ctypes.c_void_p]),
     "itr_maf_num_blocks": (ctypes.c_int64, [ctypes.c_void_p]),
     "itr_maf_num_columns": (ctypes.c_int64, [ctypes.c_void_p]),
+    "itr_maf_export": (ctypes.c_int, [ctypes.c_void_p, _u16p, _i64p, ctypes.c_int]),
     "itr_maf_symbols": (_u16p, [ctypes.c_void_p]),
     "itr_maf_offsets": (_i64p, [ctypes.c_void_p]),
     "itr_maf_num_coord_blocks": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -233,13 +233,44 @@ void do_block(const char *b, const char *e, const char *const sp[4], const size_
 
 }  // namespace
 
+// The parsed blocks stay as the worker threads left them; `off` / `coord_off` are the offsets of
+// the kept blocks in the concatenated outputs.  itr_maf_export copies them into the caller's
+// arrays with all threads (the first touch of those pages is then parallel too: at 10 bytes per
+// column the single-threaded concatenation + its page faults were half of the reader's time);
+// the pointer accessors build the concatenation on first use.
 struct itr_maf {
+    std::vector<BlockOut> outs;
+    std::vector<size_t> sym_blocks, coord_blocks;        // indices into outs of the kept blocks
     std::vector<uint16_t> sym;
     std::vector<int64_t> off{0};
     std::vector<int64_t> coord;
     std::vector<int64_t> coord_off{0};
-    bool has_coord = false;
+    bool has_coord = false, flat_sym = false, flat_coord = false;
 };
+
+static void maf_copy_out(const itr_maf *m, uint16_t *sym_out, int64_t *coord_out, int n_threads) {
+    const size_t ns = sym_out ? m->sym_blocks.size() : 0, nc = coord_out ? m->coord_blocks.size() : 0;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nt, 1), ns + nc));
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= ns + nc) break;
+            if (i < ns) {
+                const BlockOut &o = m->outs[m->sym_blocks[i]];
+                if (!o.sym.empty()) memcpy(sym_out + m->off[i], o.sym.data(), o.sym.size() * sizeof(uint16_t));
+            } else {
+                const BlockOut &o = m->outs[m->coord_blocks[i - ns]];
+                if (!o.coord.empty()) memcpy(coord_out + m->coord_off[i - ns], o.coord.data(), o.coord.size() * sizeof(int64_t));
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
 
 static int set_err(char *err, int cap, const std::string &msg, int code) {
     if (err && cap > 0) {
@@ -323,7 +354,8 @@ extern "C" int itr_maf_read(const char *path, const char *const species[4], cons
         if (cur) blocks.push_back({cur, end});
     }
     const size_t nb = blocks.size();
-    std::vector<BlockOut> outs(nb);
+    std::vector<BlockOut> &outs = m->outs;
+    outs.resize(nb);
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nt, 1), (nb + 15) / 16));
     std::atomic<size_t> next{0};
@@ -350,21 +382,19 @@ extern "C" int itr_maf_read(const char *path, const char *const species[4], cons
             delete m;
             return set_err(err, err_cap, msg, ITR_ERR_ARG);
         }
-    size_t n_sym = 0, n_coord = 0;
-    for (const BlockOut &o : outs) {
-        if (o.keep_sym) n_sym += o.sym.size();
-        if (o.keep_coord) n_coord += o.coord.size();
-    }
-    m->sym.reserve(n_sym);
-    m->coord.reserve(n_coord);
-    for (BlockOut &o : outs) {
+    int64_t n_sym = 0, n_coord = 0;
+    for (size_t i = 0; i < nb; ++i) {
+        BlockOut &o = outs[i];
+        o.dots.clear();
         if (o.keep_sym) {
-            m->sym.insert(m->sym.end(), o.sym.begin(), o.sym.end());
-            m->off.push_back((int64_t)m->sym.size());
+            m->sym_blocks.push_back(i);
+            n_sym += (int64_t)o.sym.size();
+            m->off.push_back(n_sym);
         }
         if (o.keep_coord) {
-            m->coord.insert(m->coord.end(), o.coord.begin(), o.coord.end());
-            m->coord_off.push_back((int64_t)m->coord.size());
+            m->coord_blocks.push_back(i);
+            n_coord += (int64_t)o.coord.size();
+            m->coord_off.push_back(n_coord);
         }
     }
     *out = m;
@@ -373,9 +403,33 @@ extern "C" int itr_maf_read(const char *path, const char *const species[4], cons
 
 extern "C" void itr_maf_free(itr_maf *m) { delete m; }
 extern "C" int64_t itr_maf_num_blocks(const itr_maf *m) { return m ? (int64_t)m->off.size() - 1 : 0; }
-extern "C" int64_t itr_maf_num_columns(const itr_maf *m) { return m ? (int64_t)m->sym.size() : 0; }
-extern "C" const uint16_t *itr_maf_symbols(const itr_maf *m) { return m ? m->sym.data() : nullptr; }
+extern "C" int64_t itr_maf_num_columns(const itr_maf *m) { return m ? m->off.back() : 0; }
+extern "C" int itr_maf_export(const itr_maf *m, uint16_t *sym_out, int64_t *coord_out, int n_threads) {
+    if (!m) return ITR_ERR_ARG;
+    if (coord_out && !m->has_coord) return ITR_ERR_STATE;
+    maf_copy_out(m, sym_out, coord_out, n_threads);
+    return ITR_OK;
+}
+extern "C" const uint16_t *itr_maf_symbols(const itr_maf *m) {
+    if (!m) return nullptr;
+    itr_maf *w = const_cast<itr_maf *>(m);
+    if (!w->flat_sym) {
+        w->sym.resize((size_t)m->off.back());
+        maf_copy_out(m, w->sym.data(), nullptr, 0);
+        w->flat_sym = true;
+    }
+    return m->sym.data();
+}
 extern "C" const int64_t *itr_maf_offsets(const itr_maf *m) { return m ? m->off.data() : nullptr; }
 extern "C" int64_t itr_maf_num_coord_blocks(const itr_maf *m) { return m && m->has_coord ? (int64_t)m->coord_off.size() - 1 : 0; }
-extern "C" const int64_t *itr_maf_coordinates(const itr_maf *m) { return m && m->has_coord ? m->coord.data() : nullptr; }
+extern "C" const int64_t *itr_maf_coordinates(const itr_maf *m) {
+    if (!m || !m->has_coord) return nullptr;
+    itr_maf *w = const_cast<itr_maf *>(m);
+    if (!w->flat_coord) {
+        w->coord.resize((size_t)m->coord_off.back());
+        maf_copy_out(m, nullptr, w->coord.data(), 0);
+        w->flat_coord = true;
+    }
+    return m->coord.data();
+}
 extern "C" const int64_t *itr_maf_coord_offsets(const itr_maf *m) { return m && m->has_coord ? m->coord_off.data() : nullptr; }

@@ -106,14 +106,18 @@ def read_maf(file, sp_lst, ref=None, n_threads=0):
         raise ValueError(msg)
     try:
         nb, nc = lib.itr_maf_num_blocks(handle), lib.itr_maf_num_columns(handle)
-        sym = np.ctypeslib.as_array(lib.itr_maf_symbols(handle), shape=(nc,)).copy() if nc else np.zeros(0, np.uint16)
         off = np.ctypeslib.as_array(lib.itr_maf_offsets(handle), shape=(nb + 1,)).copy()
+        sym = np.empty(nc, np.uint16)                 # filled (and first touched) by the reader's threads
         coord = coord_off = None
         if ref is not None:
             ncb = lib.itr_maf_num_coord_blocks(handle)
             coord_off = np.ctypeslib.as_array(lib.itr_maf_coord_offsets(handle), shape=(ncb + 1,)).copy()
-            n = int(coord_off[-1])
-            coord = np.ctypeslib.as_array(lib.itr_maf_coordinates(handle), shape=(n,)).copy() if n else np.zeros(0, np.int64)
+            coord = np.empty(int(coord_off[-1]), np.int64)
+        rc = lib.itr_maf_export(handle, L.as_ptr(sym, ctypes.c_uint16) if nc else None,
+                                L.as_ptr(coord, ctypes.c_int64) if coord is not None and coord.size else None,
+                                int(n_threads))
+        if rc != 0:
+            raise RuntimeError(f"itr_maf_export failed ({rc})")
     finally:
         lib.itr_maf_free(handle)
     return sym, off, coord, coord_off
